@@ -1,0 +1,184 @@
+// Tiled software RGB-D camera: stands in for `sim.render(width, height, camera_name, depth=True)` + `depth_2_meters`
+// (reference: MujocoController.py:708-740).  Output already has the reference's U/D + L/R flip applied and depth is
+// linear eye-space z in metres.
+//
+// Two kernels: (1) one warp per env runs the kinematics stage and writes every geom's world frame to HBM
+// ([N, ngeom, 12] f64); (2) one 16x16-pixel tile per CTA: the CTA culls the geoms against the tile's bounding cone into a
+// shared-memory list, then every thread casts its pixel's ray against that list (plane / sphere / box analytic, mesh geoms
+// as convex polytopes = hull face planes).  Writes are coalesced: depth f32 rows of 16 pixels, rgb u8x3.
+#pragma once
+#include "ge_physics.cuh"
+
+namespace ge {
+
+struct RenderCtx { double* gframes; size_t cap_envs; };
+
+static inline void render_init(RenderCtx& r, const DevModel&, const char*) { r.gframes = nullptr; r.cap_envs = 0; }
+static inline void render_free(RenderCtx& r) { if (r.gframes) cudaFree(r.gframes); r.gframes = nullptr; }
+
+__global__ void __launch_bounds__(32) k_render_fk(const double* qpos, int n_env, double* gframes) {
+  extern __shared__ double smem[];
+  const DevModel& m = c_m; const Layout& L = c_L;
+  int env = blockIdx.x, lane = threadIdx.x;
+  if (env >= n_env) return;
+  double* ws = smem;
+  LANE_LOOP(i, m.nq) ws[L.qpos + i] = qpos[(size_t)env * m.nq + i];
+  __syncwarp();
+  stage_fk(ws, lane);
+  double* out = gframes + (size_t)env * m.ngeom * 12;
+  LANE_LOOP(g, m.ngeom) {
+    for (int k = 0; k < 3; k++) out[12 * g + k] = ws[L.gpos + 3 * g + k];
+    for (int k = 0; k < 9; k++) out[12 * g + 3 + k] = ws[L.gmat + 9 * g + k];
+  }
+}
+
+__device__ __forceinline__ double ray_geom(int g, const double* fr, const double* o, const double* dir, double* nrm) {
+  const DevModel& m = c_m;
+  const double *gp = fr, *R = fr + 3, *size = m.geom_size + 3 * g;
+  double ol[3], dl[3], t[3];
+  v3sub(t, o, gp); m3Tmulv(ol, R, t); m3Tmulv(dl, R, dir);
+  int type = m.geom_type[g];
+  double tn = -1e300, tf = 1e300, nl[3] = {0, 0, 1};
+  if (type == G_PLANE) {
+    if (dl[2] >= -1e-12) return -1;
+    double tt = -ol[2] / dl[2];
+    if (tt <= 0) return -1;
+    m3col(nrm, R, 2);
+    return tt;
+  } else if (type == G_SPHERE) {
+    double b = v3dot(ol, dl), c = v3dot(ol, ol) - size[0] * size[0], a = v3dot(dl, dl);
+    double disc = b * b - a * c;
+    if (disc < 0) return -1;
+    double tt = (-b - sqrt(disc)) / a;
+    if (tt <= 0) return -1;
+    v3addscl(nl, ol, dl, tt); v3normalize(nl);
+    m3mulv(nrm, R, nl);
+    return tt;
+  } else if (type == G_BOX) {
+    for (int k = 0; k < 3; k++) {
+      if (fabs(dl[k]) < 1e-14) { if (fabs(ol[k]) > size[k]) return -1; continue; }
+      double t1 = (-size[k] - ol[k]) / dl[k], t2 = (size[k] - ol[k]) / dl[k], s = -1;
+      if (t1 > t2) { double x = t1; t1 = t2; t2 = x; s = 1; }
+      if (t1 > tn) { tn = t1; v3set(nl, 0, 0, 0); if (k == 0) nl[0] = s; else if (k == 1) nl[1] = s; else nl[2] = s; }
+      if (t2 < tf) tf = t2;
+    }
+    if (tn > tf || tn <= 0) return -1;
+    m3mulv(nrm, R, nl);
+    return tn;
+  } else if (type == G_MESH) {
+    int k = m.geom_meshid[g];
+    double oc[3];
+    v3sub(oc, ol, m.geom_obbcenter + 3 * g);
+    double b = v3dot(oc, dl), c = v3dot(oc, oc) - m.geom_rbound[g] * m.geom_rbound[g], a = v3dot(dl, dl);
+    if (b * b - a * c < 0) return -1;
+    const double* pl = m.mesh_faceplane + 4 * m.mesh_faceadr[k];
+    int nf = m.mesh_facenum[k];
+    for (int f = 0; f < nf; f++, pl += 4) {
+      double p0 = __ldg(pl), p1 = __ldg(pl + 1), p2 = __ldg(pl + 2), p3 = __ldg(pl + 3);
+      double dn = p0 * dl[0] + p1 * dl[1] + p2 * dl[2], on = p0 * ol[0] + p1 * ol[1] + p2 * ol[2] - p3;
+      if (fabs(dn) < 1e-14) { if (on > 0) return -1; continue; }
+      double tt = -on / dn;
+      if (dn < 0) { if (tt > tn) { tn = tt; nl[0] = p0; nl[1] = p1; nl[2] = p2; } }
+      else if (tt < tf) tf = tt;
+      if (tn > tf) return -1;
+    }
+    if (tn <= 0) return -1;
+    m3mulv(nrm, R, nl);
+    return tn;
+  }
+  return -1;
+}
+
+#define RTILE 16
+__global__ void __launch_bounds__(RTILE * RTILE) k_render(const double* gframes, int n_env, int cam, int W, int H, unsigned char* rgb, float* depth) {
+  const DevModel& m = c_m;
+  __shared__ int s_list[256];
+  __shared__ int s_n;
+  int env = blockIdx.y, tiles_x = (W + RTILE - 1) / RTILE;
+  int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  int tid = threadIdx.y * RTILE + threadIdx.x;
+  const double* fr = gframes + (size_t)env * m.ngeom * 12;
+  const double *cp = m.cam_pos0 + 3 * cam, *cm = m.cam_mat0 + 9 * cam;
+  const double PI = 3.14159265358979323846;
+  double f = 0.5 * H / tan(m.cam_fovy[cam] * PI / 360.0);
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  // tile bounding cone (camera frame): axis through the tile centre, half-angle to the farthest corner (+ half a pixel)
+  {
+    double c0 = tx * RTILE, c1 = fmin((double)W, c0 + RTILE), r0 = ty * RTILE, r1 = fmin((double)H, r0 + RTILE);
+    double ax[3] = {(0.5 * W - 0.5 * (c0 + c1)) / f, (0.5 * H - 0.5 * (r0 + r1)) / f, -1.0};
+    v3normalize(ax);
+    double cosmin = 1.0;
+    for (int k = 0; k < 4; k++) {
+      double cc = (k & 1) ? c1 : c0, rr = (k & 2) ? r1 : r0;
+      double d[3] = {(0.5 * W - cc) / f, (0.5 * H - rr) / f, -1.0};
+      v3normalize(d);
+      cosmin = fmin(cosmin, v3dot(d, ax));
+    }
+    double phi = acos(fmin(1.0, cosmin));
+    for (int g = tid; g < m.ngeom; g += RTILE * RTILE) {
+      bool pass = true;
+      if (m.geom_type[g] != G_PLANE) {
+        double cw[3], t[3], pc[3];
+        m3mulv(t, fr + 12 * g + 3, m.geom_obbcenter + 3 * g); v3add(cw, fr + 12 * g, t);
+        v3sub(t, cw, cp); m3Tmulv(pc, cm, t);
+        double dist = v3norm(pc), r = m.geom_rbound[g];
+        if (dist > r) {
+          double ang = acos(fmax(-1.0, fmin(1.0, v3dot(pc, ax) / dist)));
+          pass = ang <= phi + asin(fmin(1.0, r / dist)) + 1e-9;
+        }
+      }
+      if (pass) { int k = atomicAdd(&s_n, 1); if (k < 256) s_list[k] = g; }
+    }
+  }
+  __syncthreads();
+  int c = tx * RTILE + threadIdx.x, r = ty * RTILE + threadIdx.y;
+  if (c >= W || r >= H) return;
+  int n = s_n < 256 ? s_n : 256;
+  double dc[3] = {(0.5 * W - c - 0.5) / f, (0.5 * H - r - 0.5) / f, -1.0}, dir[3];
+  m3mulv(dir, cm, dc);
+  double best = 1e300, bn[3] = {0, 0, 1};
+  int bg = -1;
+  for (int k = 0; k < n; k++) {
+    int g = s_list[k];
+    double nr[3];
+    double t = ray_geom(g, fr + 12 * g, cp, dir, nr);
+    if (t > 0 && (t < best || (t == best && g < bg))) { best = t; bg = g; v3copy(bn, nr); }
+  }
+  size_t px = ((size_t)env * H + r) * W + c;
+  if (bg < 0) { depth[px] = (float)(m.zfar * m.extent); rgb[3 * px] = rgb[3 * px + 1] = rgb[3 * px + 2] = 0; return; }
+  depth[px] = (float)best;
+  double light[3] = {-1, 1, -2.565};
+  v3normalize(light);
+  double lam = -v3dot(bn, light);
+  if (lam < 0) lam = 0;
+  double shade = 0.4 + 0.6 * lam;
+  const double* col = m.geom_rgba + 4 * bg;
+  double base[3] = {col[0], col[1], col[2]};
+  if (m.geom_type[bg] == G_PLANE) {
+    double hit[3];
+    v3addscl(hit, cp, dir, best);
+    int cx = (int)floor(hit[0] / 0.25), cy = (int)floor(hit[1] / 0.25);
+    if ((cx + cy) & 1) { base[0] = 0.1; base[1] = 0.2; base[2] = 0.3; } else { base[0] = 0.2; base[1] = 0.3; base[2] = 0.4; }
+  }
+  for (int k = 0; k < 3; k++) { double v = base[k] * shade * 255.0 + 0.5; rgb[3 * px + k] = (unsigned char)(v > 255 ? 255 : v); }
+}
+
+static inline int render_launch(RenderCtx& rc, const DevModel& m, const Layout& L, const double* qpos, int n_env, int cam, int W, int H,
+                                unsigned char* rgb, float* depth, cudaStream_t stream, int64_t* launches) {
+  if (rc.cap_envs < (size_t)n_env) {
+    if (rc.gframes) cudaFree(rc.gframes);
+    if (cudaMalloc(&rc.gframes, sizeof(double) * 12 * m.ngeom * (size_t)n_env) != cudaSuccess) return -1;
+    rc.cap_envs = n_env;
+  }
+  static bool attr_done = false;
+  if (!attr_done && L.total_bytes > 48 * 1024) { cudaFuncSetAttribute(k_render_fk, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes); attr_done = true; }
+  k_render_fk<<<n_env, 32, L.total_bytes, stream>>>(qpos, n_env, rc.gframes);
+  int tiles = ((W + RTILE - 1) / RTILE) * ((H + RTILE - 1) / RTILE);
+  dim3 grid(tiles, n_env), blk(RTILE, RTILE);
+  k_render<<<grid, blk, 0, stream>>>(rc.gframes, n_env, cam, W, H, rgb, depth);
+  *launches += 2;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace ge

@@ -445,6 +445,35 @@ def compile_mjcf(path):
     M["cam_mat0"] = np.array([rigid.quat_to_mat(c["quat"]).reshape(9) for c in cameras]).reshape(-1, 9)
     M["cam_fovy"] = np.array([c["fovy"] for c in cameras])
 
+    # ---- traversal tables for the warp-parallel kernels (bodies and dofs are numbered depth-first, so every
+    # subtree is a contiguous index range)
+    body_subtreenum = np.ones(nbody, np.int32)
+    for bid in range(nbody - 1, 0, -1):
+        body_subtreenum[bodies[bid]["parent"]] += body_subtreenum[bid]
+    dof_subtreenum = np.ones(nv, np.int32)
+    dof_depth = np.zeros(nv, np.int32)
+    for d in range(nv - 1, -1, -1):
+        if dof_parent[d] >= 0:
+            dof_subtreenum[dof_parent[d]] += dof_subtreenum[d]
+    for d in range(nv):
+        dof_depth[d] = 0 if dof_parent[d] < 0 else dof_depth[dof_parent[d]] + 1
+    tree_roots = [d for d in range(nv) if dof_parent[d] < 0]
+    M["body_subtreenum"] = body_subtreenum
+    M["dof_subtreenum"] = dof_subtreenum
+    M["dof_depth"] = dof_depth
+    M["tree_dofadr"] = np.array(tree_roots, np.int32)
+    M["tree_dofnum"] = np.array([dof_subtreenum[d] for d in tree_roots], np.int32)
+    M["ntree"] = len(tree_roots)
+    M["geom_lmat"] = np.array([rigid.quat_to_mat(g["quat"]).reshape(9) for g in geoms]).reshape(ngeom, 9)
+    # outward face planes of every hull (normal, offset), geom-local: used by the ray-caster
+    planes = []
+    for m_ in meshes:
+        hv, hf = m_["hull_vert"], m_["hull_face"]
+        nrm = np.cross(hv[hf[:, 1]] - hv[hf[:, 0]], hv[hf[:, 2]] - hv[hf[:, 0]])
+        nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-300)
+        planes.append(np.concatenate([nrm, np.einsum("ij,ij->i", nrm, hv[hf[:, 0]])[:, None]], axis=1))
+    M["mesh_faceplane"] = np.concatenate(planes) if planes else np.zeros((0, 4))
+
     # ---- quantities derived at qpos0: invweight0, mean inertia, extent
     kin = rigid.Kinematics(M)
     Mq = kin.mass_matrix(qpos0)

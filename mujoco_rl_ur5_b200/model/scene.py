@@ -41,6 +41,9 @@ def compile_scene(key, reference_dir=None):
     M["ik_chain"], M["ik_lower"], M["ik_upper"], M["ik_offset"] = IK_CHAIN, IK_LOWER, IK_UPPER, IK_OFFSET
     M["ik_base_body"] = names["body"].index("base_link")
     M["ee_body"] = names["body"].index("ee_link")
+    # base_link is welded to the world: its world position is a model constant (used by the IK, MujocoController.py:488)
+    from .rigid import Kinematics
+    M["ik_base_pos"] = Kinematics(M).forward(M["qpos0"])["xpos"][M["ik_base_body"]]
     M["cam_top_down"] = names["camera"].index("top_down")
     mats = M.pop("_materials", None)
     rgba = np.array(M["geom_rgba"], dtype=np.float64)

@@ -780,11 +780,18 @@ static void col_convex(Env* e, int pair, int g1, int g2) {
   add_contact(e, pair, dist, pos, dir);
 }
 
+static int pair_is_analytic(int t1, int t2) {
+  return t1 == G_PLANE || (t1 == G_SPHERE && (t2 == G_SPHERE || t2 == G_BOX)) || (t1 == G_BOX && t2 == G_BOX);
+}
+/* Two passes over the static candidate list: analytic pair functions first, then the generic convex (MPR) pairs.
+ * (Contact order only affects floating-point summation order in the solver; the CUDA engine emits the same order.) */
 static void collision(Env* e) {
   const Model* m = e->m;
   e->ncon = 0; e->con_overflow = 0;
+  for (int pass = 0; pass < 2; pass++)
   for (int p = 0; p < m->npair; p++) {
     int g1 = m->pair_geom[2 * p], g2 = m->pair_geom[2 * p + 1], t1 = m->geom_type[g1], t2 = m->geom_type[g2];
+    if (pair_is_analytic(t1, t2) != (pass == 0)) continue;
     double margin = m->pair_margin[p], c1[3], c2[3], t[3];
     m3mulv(t, e->gmat + 9 * g2, m->geom_obbcenter + 3 * g2); v3add(c2, e->gpos + 3 * g2, t);
     if (t1 == G_PLANE) {

@@ -1,0 +1,27 @@
+"""Shared helpers for the parity tests: deterministic resets and action replays (SURVEY 8(d) seeds)."""
+import numpy as np
+
+HOME = np.array([0, -1.57, 1.57, -1.57, -1.57, 0.0, 0.3])  # GraspingEnv.py:418
+
+
+def reset_qpos_scene_a(A, env_index):
+    """Scene-A reset = the commented IT4 rule (GraspingEnv.py:435-463): x~U(-.25,.25), y~U(-.17,.17), z=0, identity quat;
+    RNG = RandomState(20000 + env_index), objects in joint order, draws x then y."""
+    rng = np.random.RandomState(20000 + env_index)
+    q = np.array(A["qpos0"], dtype=np.float64).copy()
+    q[:7] = HOME
+    q[7] = 0.3  # right knuckle follows the equality constraint
+    nobj = (int(A["nq"]) - 8) // 7
+    for i in range(nobj):
+        a = 8 + 7 * i
+        q[a] = rng.uniform(-0.25, 0.25)
+        q[a + 1] = rng.uniform(-0.17, 0.17)
+        q[a + 2] = 0.0
+        q[a + 3:a + 7] = [1, 0, 0, 0]
+    return q
+
+
+def object_positions(A, qpos):
+    nobj = (int(A["nq"]) - 8) // 7
+    first = int(A["nbody"]) - nobj
+    return np.array([qpos[8 + 7 * i:11 + 7 * i] + A["body_pos"][first + i] for i in range(nobj)])
