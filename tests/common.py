@@ -11,7 +11,7 @@ def reset_qpos_scene_a(A, env_index):
     q = np.array(A["qpos0"], dtype=np.float64).copy()
     q[:7] = HOME
     q[7] = 0.3  # right knuckle follows the equality constraint
-    nobj = (int(A["nq"]) - 8) // 7
+    nobj = (int(np.asarray(A["nq"]).ravel()[0]) - 8) // 7
     for i in range(nobj):
         a = 8 + 7 * i
         q[a] = rng.uniform(-0.25, 0.25)
@@ -22,6 +22,6 @@ def reset_qpos_scene_a(A, env_index):
 
 
 def object_positions(A, qpos):
-    nobj = (int(A["nq"]) - 8) // 7
-    first = int(A["nbody"]) - nobj
+    nobj = (int(np.asarray(A["nq"]).ravel()[0]) - 8) // 7
+    first = int(np.asarray(A["nbody"]).ravel()[0]) - nobj
     return np.array([qpos[8 + 7 * i:11 + 7 * i] + A["body_pos"][first + i] for i in range(nobj)])

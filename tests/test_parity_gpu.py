@@ -7,7 +7,7 @@ rounding differences) and the north-star tolerance (joint angles 1e-4, flags bit
 import numpy as np
 import pytest
 
-from tests.common import object_positions, reset_qpos_scene_a
+from tests.common import HOME, object_positions, reset_qpos_scene_a
 
 pytestmark = pytest.mark.gpu
 
@@ -82,7 +82,8 @@ def test_substep_trajectory_parity(scene_a, engine4):
     blob, A, _ = scene_a
     qpos, _ = _settled_states(scene_a, 4, 0)
     engine4.set_state(qpos)
-    engine4.move_group("All", None, 1e-7, 300)
+    tgt = np.tile(HOME + np.array([0.3, 0.2, -0.2, 0.1, 0.1, 0.5, -0.1]), (4, 1))
+    engine4.move_group("All", tgt, 1e-7, 300)
     assert engine4.run() == 0
     gq, gv = engine4.get_state()
     gq, gv = gq.cpu().numpy(), gv.cpu().numpy()
@@ -91,7 +92,7 @@ def test_substep_trajectory_parity(scene_a, engine4):
     for env in range(4):
         o = _oracle(blob)
         o.reset(qpos[env])
-        r, s = o.move_group("All", None, 1e-7, 300)
+        r, s = o.move_group("All", tgt[env], 1e-7, 300)
         assert (r, s) == (2, 301)
         assert np.abs(gq[env] - o.qpos).max() < 1e-6, (env, np.abs(gq[env] - o.qpos).max())
         assert np.abs(gv[env] - o.qvel).max() < 1e-4
