@@ -80,6 +80,8 @@ int ge_get_results(ge_handle h, int32_t* result, int32_t* steps, uint8_t* reward
 /* per-phase step counts of the last ge_grasp program: info [N,12] int32 [dev] (same layout as the oracle's info[]) */
 int ge_get_grasp_info(ge_handle h, int32_t* info);
 int ge_get_status(ge_handle h, int32_t* status /*[N] dev*/);
+/* busy [N] u8 [dev]: 1 while the env still has a movement or program pending (i.e. ge_run would advance it) */
+int ge_get_busy(ge_handle h, uint8_t* busy);
 
 /* MJ_Controller.ik (MujocoController.py:467-517): xyz [N,3] -> q5 [N,5], ok [N] u8 (all [dev]) */
 int ge_ik(ge_handle h, const double* xyz, double* q5, uint8_t* ok);

@@ -16,7 +16,7 @@ _LIB = None
 SYMBOLS = [
     "ge_last_error", "ge_version", "ge_create", "ge_destroy", "ge_size", "ge_set_state", "ge_get_state", "ge_get_body_xpos",
     "ge_set_gain", "ge_move_group", "ge_move_ee", "ge_stay", "ge_grasp", "ge_run", "ge_run_async", "ge_get_results",
-    "ge_get_grasp_info", "ge_get_status", "ge_ik", "ge_pixel_2_world", "ge_render", "ge_debug_forward", "ge_counters",
+    "ge_get_grasp_info", "ge_get_status", "ge_get_busy", "ge_ik", "ge_pixel_2_world", "ge_render", "ge_debug_forward", "ge_counters",
 ]
 GROUPS = {"All": 0x7F, "Arm": 0x1F, "Gripper": 0x40}
 MOVE_RESULT = {0: "", 1: "success", 2: "max. steps reached: {}", 3: "No valid joint angles received, could not move EE to position."}
@@ -52,6 +52,7 @@ def load_library():
         L.ge_get_results.argtypes = [P, P, P, P, P]
         L.ge_get_grasp_info.argtypes = [P, P]
         L.ge_get_status.argtypes = [P, P]
+        L.ge_get_busy.argtypes = [P, P]
         L.ge_ik.argtypes = [P, P, P, P]
         L.ge_pixel_2_world.argtypes = [P, C.c_int, C.c_int, C.c_int, P, P, P, P]
         L.ge_render.argtypes = [P, C.c_int, C.c_int, C.c_int, P, P]
@@ -210,6 +211,12 @@ class BatchedEngine:
         st = t.empty(self.n_envs, dtype=t.int32, device=self.device)
         self._ck(self.L.ge_get_status(self.h, _ptr(st)), "ge_get_status")
         return st
+
+    def busy(self):
+        t = self.torch
+        b = t.empty(self.n_envs, dtype=t.uint8, device=self.device)
+        self._ck(self.L.ge_get_busy(self.h, _ptr(b)), "ge_get_busy")
+        return b
 
     # ------------------------------------------------------------------ camera / IK
     def ik(self, xyz):
