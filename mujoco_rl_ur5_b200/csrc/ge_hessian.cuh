@@ -1,0 +1,271 @@
+// Newton Hessian  H = M + J^T D_active J  and its Cholesky solve, exploiting the block structure of the scene.
+//
+// The mass matrix is block diagonal over kinematic trees (the arm + one block per object).  A contact couples two trees
+// only when both of its bodies are dynamic and belong to different trees.  Trees that no such contact (or equality row)
+// touches are "uncoupled": their Hessian block is assembled, factorised and solved by ONE lane each, all such trees in
+// parallel (lane t <-> tree t) with a plain dense left-looking Cholesky.  Only the coupled trees (e.g. arm + grasped object)
+// go through the warp-cooperative skyline routine.  Included by ge_solver.cuh.
+#pragma once
+
+#define HIDX(i, j) (((i) * ((i) + 1)) / 2 + (j))
+#define GE_MAXE 16  // dofs of one contact after removing the common ancestors of the two chains
+
+namespace ge {
+
+__device__ __forceinline__ int tree_of_body(int b) {
+  int d = c_m.body_lastdof[b];
+  return d < 0 ? -1 : c_m.dof_treeindex[d];
+}
+
+// active-set weights applied to one Jacobian column: t = W J  (W00 = D nact, W0k = D mu_k (a+ - a-), Wkk = D mu_k^2 (a+ + a-))
+__device__ __forceinline__ void weight_column(const double* c, int dim, int mask, const double* J, double* t) {
+  double D = c[C_D];
+  if (dim == 1) { t[0] = D * J[0]; return; }
+  int nact = __popc(mask);
+  double t0 = nact * J[0];
+  for (int k = 1; k < dim; k++) {
+    int ap = (mask >> (2 * (k - 1))) & 1, an = (mask >> (2 * (k - 1) + 1)) & 1;
+    double mu = c[C_MU + k - 1];
+    t0 += mu * (ap - an) * J[k];
+    t[k] = D * mu * ((ap - an) * J[0] + mu * (ap + an) * J[k]);
+  }
+  t[0] = D * t0;
+}
+__device__ __forceinline__ void jac_column(const double* c, int dim, const double* cd, double sgn, double* J) {
+  double pu[3];
+  for (int k = 0; k < dim; k++) {
+    if (k < 3) { v3cross(pu, c + C_POS, c + C_FRAME + 3 * k); J[k] = sgn * (v3dot(c + C_FRAME + 3 * k, cd + 3) + v3dot(pu, cd)); }
+    else J[k] = sgn * v3dot(c + C_FRAME + 3 * (k - 3), cd);
+  }
+}
+
+__device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int nsr, int lane) {
+  const DevModel& m = c_m; const Layout& L = c_L;
+  double* H = ws + L.H;
+  const double *qM = ws + L.qM, *cdof = ws + L.cdof;
+  int *first = wi + L.i_first, *tcoupled = wi + L.i_tcoupled;
+  // ---- which trees are coupled to another tree by an active constraint
+  // GE_TREE_LOCAL=1 enables the one-lane-per-uncoupled-tree path.  Measured on B200 (r01): it halves throughput (a single
+  // lane walking a 6x6 block serially is latency-bound while 25 lanes idle), so the default treats every tree as coupled and
+  // uses the warp-cooperative path for all of them; the block structure still pays through the per-row envelopes.
+#ifndef GE_TREE_LOCAL
+#define GE_TREE_LOCAL 0
+#endif
+  LANE_LOOP(t, m.ntree) tcoupled[t] = GE_TREE_LOCAL ? 0 : 1;
+  __syncwarp();
+  LANE_LOOP(ci, ncon) {
+    if (!wi[L.i_cact + ci]) continue;
+    int t1 = tree_of_body(wi[L.i_cb1 + ci]), t2 = tree_of_body(wi[L.i_cb2 + ci]);
+    if (t1 >= 0 && t2 >= 0 && t1 != t2) { tcoupled[t1] = 1; tcoupled[t2] = 1; }
+  }
+  LANE_LOOP(i, nsr) {
+    if (!wi[L.i_sract + i]) continue;
+    int A = wi[L.i_srA + i], B = wi[L.i_srB + i];
+    if (B >= 0 && m.dof_treeindex[A] != m.dof_treeindex[B]) { tcoupled[m.dof_treeindex[A]] = 1; tcoupled[m.dof_treeindex[B]] = 1; }
+  }
+  __syncwarp();
+  // ---- rows of M (zero-filled down to the tree root = dense block envelope)
+  LANE_LOOP(i, m.nv) {
+    int root = m.tree_dofadr[m.dof_treeindex[i]];
+    for (int j = root; j <= i; j++) H[HIDX(i, j)] = 0;
+    int a = m.dof_Madr[i], k = 0;
+    for (int j = i; j >= 0; j = m.dof_parentid[j], k++) H[HIDX(i, j)] = qM[a + k];
+    first[i] = root;
+  }
+  __syncwarp();
+  // ---- uncoupled trees: one lane per tree adds the contacts (and simple rows) that live entirely inside its block
+  LANE_LOOP(t, m.ntree) {
+    if (tcoupled[t]) continue;
+    for (int ci = 0; ci < ncon; ci++) {
+      int mask = wi[L.i_cact + ci];
+      if (!mask) continue;
+      int b1 = wi[L.i_cb1 + ci], b2 = wi[L.i_cb2 + ci];
+      if (tree_of_body(b1) != t && tree_of_body(b2) != t) continue;
+      const double* c = ws + L.con + ci * L.cstride;
+      int dim = wi[L.i_cdim + ci];
+      int E[GE_MAXE];
+      double Jc[GE_MAXE][6], Tc[GE_MAXE][6];
+      int i1 = m.body_lastdof[b1], i2 = m.body_lastdof[b2], n = 0;
+      while (i1 != i2 && n < GE_MAXE) {
+        int e; double s;
+        if (i2 > i1) { e = i2; s = 1.0; i2 = m.dof_parentid[i2]; } else { e = i1; s = -1.0; i1 = m.dof_parentid[i1]; }
+        E[n] = e;
+        jac_column(c, dim, cdof + 6 * e, s, Jc[n]);
+        weight_column(c, dim, mask, Jc[n], Tc[n]);
+        n++;
+      }
+      for (int a = 0; a < n; a++)
+        for (int b = 0; b < n; b++) {
+          if (E[a] < E[b]) continue;
+          double h = 0;
+          for (int k = 0; k < dim; k++) h += Tc[a][k] * Jc[b][k];
+          H[HIDX(E[a], E[b])] += h;
+        }
+    }
+    for (int i = 0; i < nsr; i++) {
+      if (!wi[L.i_sract + i]) continue;
+      int A = wi[L.i_srA + i], B = wi[L.i_srB + i];
+      if (m.dof_treeindex[A] != t) continue;
+      double D = srv(ws, SR_D, i), ca = srv(ws, SR_CA, i), cb = srv(ws, SR_CB, i);
+      H[HIDX(A, A)] += D * ca * ca;
+      if (B >= 0) {
+        H[HIDX(B, B)] += D * cb * cb;
+        int hi = A > B ? A : B, lo = A > B ? B : A;
+        H[HIDX(hi, lo)] += D * ca * cb;
+      }
+    }
+  }
+  __syncwarp();
+  bool any_coupled = false;
+  for (int t = 0; t < m.ntree; t++) any_coupled |= tcoupled[t] != 0;
+  if (!any_coupled) return;
+  // ---- coupled trees, pass 1: row envelopes (a coupled row reaches down to the lowest dof it shares a contact with) ...
+  for (int ci = 0; ci < ncon; ci++) {
+    if (!wi[L.i_cact + ci]) continue;
+    int b1 = wi[L.i_cb1 + ci], b2 = wi[L.i_cb2 + ci], t1 = tree_of_body(b1), t2 = tree_of_body(b2);
+    if (!((t1 >= 0 && tcoupled[t1]) || (t2 >= 0 && tcoupled[t2]))) continue;
+    int i1 = m.body_lastdof[b1], i2 = m.body_lastdof[b2], n = 0, mydof = -1, minE = 0x7fffffff;
+    while (i1 != i2) {
+      int e;
+      if (i2 > i1) { e = i2; i2 = m.dof_parentid[i2]; } else { e = i1; i1 = m.dof_parentid[i1]; }
+      if (n == lane) mydof = e;
+      if (e < minE) minE = e;
+      n++;
+    }
+    if (lane < n && first[mydof] > minE) first[mydof] = minE;
+    __syncwarp();
+  }
+  if (lane == 0)
+    for (int i = 0; i < nsr; i++) {
+      if (!wi[L.i_sract + i]) continue;
+      int A = wi[L.i_srA + i], B = wi[L.i_srB + i];
+      if (B < 0 || !tcoupled[m.dof_treeindex[A]]) continue;
+      int hi = A > B ? A : B, lo = A > B ? B : A;
+      if (first[hi] > lo) first[hi] = lo;
+    }
+  __syncwarp();
+  // ... and the zero fill of the part of each row below its own tree block
+  LANE_LOOP(i, m.nv) {
+    int root = m.tree_dofadr[m.dof_treeindex[i]];
+    for (int j = first[i]; j < root; j++) H[HIDX(i, j)] = 0;
+  }
+  __syncwarp();
+  // ---- pass 2: warp-cooperative accumulation, one lane per dof of the contact
+  for (int ci = 0; ci < ncon; ci++) {
+    int mask = wi[L.i_cact + ci];
+    if (!mask) continue;
+    int b1 = wi[L.i_cb1 + ci], b2 = wi[L.i_cb2 + ci], t1 = tree_of_body(b1), t2 = tree_of_body(b2);
+    if (!((t1 >= 0 && tcoupled[t1]) || (t2 >= 0 && tcoupled[t2]))) continue;
+    const double* c = ws + L.con + ci * L.cstride;
+    int dim = wi[L.i_cdim + ci];
+    int i1 = m.body_lastdof[b1], i2 = m.body_lastdof[b2], n = 0, mydof = -1, minE = 0x7fffffff;
+    double mysgn = 0;
+    while (i1 != i2) {
+      int e; double s;
+      if (i2 > i1) { e = i2; s = 1.0; i2 = m.dof_parentid[i2]; } else { e = i1; s = -1.0; i1 = m.dof_parentid[i1]; }
+      if (n == lane) { mydof = e; mysgn = s; }
+      if (e < minE) minE = e;
+      n++;
+    }
+    double J[6] = {0, 0, 0, 0, 0, 0}, t[6] = {0, 0, 0, 0, 0, 0};
+    if (lane < n) {
+      jac_column(c, dim, cdof + 6 * mydof, mysgn, J);
+      weight_column(c, dim, mask, J, t);
+    }
+    for (int j = 0; j < n; j++) {
+      int dj = __shfl_sync(FULL, mydof, j);
+      double h = 0;
+      for (int k = 0; k < dim; k++) h += t[k] * __shfl_sync(FULL, J[k], j);
+      if (lane < n && mydof >= dj) H[HIDX(mydof, dj)] += h;
+    }
+    __syncwarp();
+  }
+  if (lane == 0)
+    for (int i = 0; i < nsr; i++) {
+      if (!wi[L.i_sract + i]) continue;
+      int A = wi[L.i_srA + i], B = wi[L.i_srB + i];
+      if (!tcoupled[m.dof_treeindex[A]]) continue;
+      double D = srv(ws, SR_D, i), ca = srv(ws, SR_CA, i), cb = srv(ws, SR_CB, i);
+      H[HIDX(A, A)] += D * ca * ca;
+      if (B >= 0) {
+        H[HIDX(B, B)] += D * cb * cb;
+        int hi = A > B ? A : B, lo = A > B ? B : A;
+        H[HIDX(hi, lo)] += D * ca * cb;
+      }
+    }
+  __syncwarp();
+}
+
+// x := -H^-1 g.  Uncoupled trees: dense left-looking Cholesky + substitutions, one lane per tree.  Coupled trees: skyline
+// right-looking Cholesky with the whole warp (each lane owns rows lane, lane+32, ...).
+__device__ __noinline__ void cholesky_solve(double* ws, const int* wi, double* x, const double* g, int lane) {
+  const DevModel& m = c_m; const Layout& L = c_L;
+  double* H = ws + L.H;
+  const int *first = wi + L.i_first, *tcoupled = wi + L.i_tcoupled;
+  int nv = m.nv;
+  bool any_coupled = false;
+  for (int t = 0; t < m.ntree; t++) any_coupled |= tcoupled[t] != 0;
+  LANE_LOOP(t, m.ntree) {
+    if (tcoupled[t]) continue;
+    int lo = m.tree_dofadr[t], hi = lo + m.tree_dofnum[t];
+    for (int j = lo; j < hi; j++) {
+      double s = H[HIDX(j, j)];
+      for (int k = lo; k < j; k++) { double l = H[HIDX(j, k)]; s -= l * l; }
+      if (s < GE_MINVAL) s = GE_MINVAL;
+      double ljj = sqrt(s), inv = 1.0 / ljj;
+      H[HIDX(j, j)] = ljj;
+      for (int i = j + 1; i < hi; i++) {
+        double tt = H[HIDX(i, j)];
+        for (int k = lo; k < j; k++) tt -= H[HIDX(i, k)] * H[HIDX(j, k)];
+        H[HIDX(i, j)] = tt * inv;
+      }
+    }
+    for (int i = lo; i < hi; i++) { double y = g[i]; for (int k = lo; k < i; k++) y -= H[HIDX(i, k)] * x[k]; x[i] = y / H[HIDX(i, i)]; }
+    for (int i = hi - 1; i >= lo; i--) { double y = x[i]; for (int k = i + 1; k < hi; k++) y -= H[HIDX(k, i)] * x[k]; x[i] = y / H[HIDX(i, i)]; }
+    for (int i = lo; i < hi; i++) x[i] = -x[i];
+  }
+  __syncwarp();
+  if (!any_coupled) return;
+  for (int j = 0; j < nv; j++) {
+    if (!tcoupled[m.dof_treeindex[j]]) continue;
+    double d = H[HIDX(j, j)];
+    if (d < GE_MINVAL) d = GE_MINVAL;
+    double ljj = sqrt(d), inv = 1.0 / ljj;
+    __syncwarp();
+    for (int i = j + 1 + lane; i < nv; i += 32)
+      if (first[i] <= j) H[HIDX(i, j)] *= inv;
+    if (lane == 0) H[HIDX(j, j)] = ljj;
+    __syncwarp();
+    for (int i = j + 1 + lane; i < nv; i += 32) {
+      if (first[i] > j) continue;
+      double lij = H[HIDX(i, j)];
+      if (lij == 0.0) continue;
+      for (int k = j + 1; k <= i; k++)
+        if (first[k] <= j) H[HIDX(i, k)] -= lij * H[HIDX(k, j)];
+    }
+    __syncwarp();
+  }
+  LANE_LOOP(i, nv) if (tcoupled[m.dof_treeindex[i]]) x[i] = g[i];
+  __syncwarp();
+  for (int j = 0; j < nv; j++) {  // L y = g, column oriented
+    if (!tcoupled[m.dof_treeindex[j]]) continue;
+    double yj = x[j] / H[HIDX(j, j)];
+    __syncwarp();
+    if (lane == 0) x[j] = yj;
+    for (int i = j + 1 + lane; i < nv; i += 32)
+      if (first[i] <= j) x[i] -= H[HIDX(i, j)] * yj;
+    __syncwarp();
+  }
+  for (int i = nv - 1; i >= 0; i--) {  // L^T x = y, column oriented
+    if (!tcoupled[m.dof_treeindex[i]]) continue;
+    double xi = x[i] / H[HIDX(i, i)];
+    __syncwarp();
+    if (lane == 0) x[i] = xi;
+    for (int k = first[i] + lane; k < i; k += 32) x[k] -= H[HIDX(i, k)] * xi;
+    __syncwarp();
+  }
+  LANE_LOOP(i, nv) if (tcoupled[m.dof_treeindex[i]]) x[i] = -x[i];
+  __syncwarp();
+}
+
+}  // namespace ge

@@ -20,7 +20,7 @@ __constant__ Layout c_L;
 // ------------------------------------------------------------------------------------------------ kinematics
 // Three lane-parallel phases, no level synchronisation: (1) every body's transform relative to its parent,
 // (2) every body composes its own ancestor chain, (3) motion axes / spatial inertias / geom frames.
-__device__ __forceinline__ void stage_fk(double* ws, int lane) {
+__device__ __noinline__ void stage_fk(double* ws, int lane) {
   const DevModel& m = c_m; const Layout& L = c_L;
   const double* qpos = ws + L.qpos;
   double *lpos = ws + L.lpos, *lquat = ws + L.lquat, *janchor = ws + L.janchor, *jaxis = ws + L.jaxis;
@@ -118,7 +118,7 @@ __device__ __forceinline__ void stage_fk(double* ws, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------------ bias forces (RNE) -> ws[qfrc_smooth] := qfrc_bias
-__device__ __forceinline__ void stage_rne(double* ws, int lane) {
+__device__ __noinline__ void stage_rne(double* ws, int lane) {
   const DevModel& m = c_m; const Layout& L = c_L;
   const double *qvel = ws + L.qvel, *cdof = ws + L.cdof, *cinert = ws + L.cinert;
   double *cdofdot = ws + L.cdofdot, *cvel = ws + L.cvel, *cacc = ws + L.cacc, *cfrc = ws + L.cfrc;
@@ -160,7 +160,7 @@ __device__ __forceinline__ void stage_rne(double* ws, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------------ CRBA -> qM (tree-sparse rows: self, parent, grandparent, ...)
-__device__ __forceinline__ void stage_crb(double* ws, int lane) {
+__device__ __noinline__ void stage_crb(double* ws, int lane) {
   const DevModel& m = c_m; const Layout& L = c_L;
   const double *cdof = ws + L.cdof, *cinert = ws + L.cinert;
   double *crb = ws + L.cvel, *qM = ws + L.qM;  // composite inertias reuse the (dead) cvel/cacc area
@@ -183,7 +183,7 @@ __device__ __forceinline__ void stage_crb(double* ws, int lane) {
 }
 
 // L^T D L factorisation / solve of the tree-sparse mass matrix; one lane per kinematic tree (trees are independent)
-__device__ __forceinline__ void factor_trees(double* LD, int lane) {
+__device__ __noinline__ void factor_trees(double* LD, int lane) {
   const DevModel& m = c_m;
   LANE_LOOP(t, m.ntree) {
     int lo = m.tree_dofadr[t], hi = lo + m.tree_dofnum[t];
@@ -200,7 +200,7 @@ __device__ __forceinline__ void factor_trees(double* LD, int lane) {
   }
   __syncwarp();
 }
-__device__ __forceinline__ void solve_trees(const double* LD, double* x, int lane) {
+__device__ __noinline__ void solve_trees(const double* LD, double* x, int lane) {
   const DevModel& m = c_m;
   LANE_LOOP(t, m.ntree) {
     int lo = m.tree_dofadr[t], hi = lo + m.tree_dofnum[t];
@@ -220,7 +220,7 @@ __device__ __forceinline__ void solve_trees(const double* LD, double* x, int lan
   __syncwarp();
 }
 // r = M v, one lane per dof (ancestors from the dof's own row, descendants from theirs)
-__device__ __forceinline__ void mul_M(const double* qM, double* r, const double* v, int lane) {
+__device__ __noinline__ void mul_M(const double* qM, double* r, const double* v, int lane) {
   const DevModel& m = c_m;
   LANE_LOOP(i, m.nv) {
     int a = m.dof_Madr[i], k = 1;
@@ -274,7 +274,7 @@ __device__ __forceinline__ void col_plane_sphere(const double* ws, int g1, int g
   v3addscl(out.pos[0], gpos + 3 * g2, n, -(r + 0.5 * dist));
   out.dist[0] = dist; out.n = 1;
 }
-__device__ __forceinline__ void col_plane_box(const double* ws, int g1, int g2, double margin, PairContacts& out) {
+__device__ __noinline__ void col_plane_box(const double* ws, int g1, int g2, double margin, PairContacts& out) {
   const DevModel& m = c_m; const Layout& L = c_L;
   const double *gpos = ws + L.gpos, *gmat = ws + L.gmat;
   double n[3];
@@ -291,7 +291,7 @@ __device__ __forceinline__ void col_plane_box(const double* ws, int g1, int g2, 
     out.dist[out.n] = dist; out.n++;
   }
 }
-__device__ __forceinline__ void col_plane_mesh(const double* ws, int g1, int g2, double margin, PairContacts& out) {
+__device__ __noinline__ void col_plane_mesh(const double* ws, int g1, int g2, double margin, PairContacts& out) {
   const DevModel& m = c_m; const Layout& L = c_L;
   const double *gpos = ws + L.gpos, *gmat = ws + L.gmat;
   double n[3], nl[3];
@@ -322,7 +322,7 @@ __device__ __forceinline__ void col_sphere_sphere(const double* ws, int g1, int 
   v3addscl(out.pos[0], gpos + 3 * g1, d, r1 + 0.5 * dist);
   out.dist[0] = dist; out.n = 1;
 }
-__device__ __forceinline__ void col_sphere_box(const double* ws, int g1, int g2, double margin, PairContacts& out) {
+__device__ __noinline__ void col_sphere_box(const double* ws, int g1, int g2, double margin, PairContacts& out) {
   const DevModel& m = c_m; const Layout& L = c_L;
   const double *gpos = ws + L.gpos, *gmat = ws + L.gmat;
   const double* h = m.geom_size + 3 * g2;
@@ -468,7 +468,7 @@ __device__ __noinline__ void col_box_box(const double* ws, int g1, int g2, doubl
 // ---- warp-cooperative Minkowski Portal Refinement: every lane carries the same portal, the hull support function is a
 // 32-lane strided arg-max over the vertices followed by a butterfly reduction (lowest index wins ties, like the oracle's scan)
 struct SP { double v[3], a[3], b[3]; };
-__device__ __forceinline__ void support_w(const double* ws, int g, double inflate, const double* dir, double* out, int lane) {
+__device__ __noinline__ void support_w(const double* ws, int g, double inflate, const double* dir, double* out, int lane) {
   const DevModel& m = c_m; const Layout& L = c_L;
   const double *R = ws + L.gmat + 9 * g, *size = m.geom_size + 3 * g;
   double dl[3], pl[3] = {0, 0, 0};
@@ -602,7 +602,7 @@ __device__ __forceinline__ void make_frame(double* fr) {
 // Broad phase over the static candidate pair list (bounding spheres, then oriented boxes), analytic narrow phase one lane
 // per surviving pair, then the MPR pairs one after the other with the whole warp.  Returns the number of contacts; sets
 // bit 0 of *status on overflow.  (The oracle emits contacts in the same order: analytic pairs first, then MPR pairs.)
-__device__ __forceinline__ int stage_collision(double* ws, int* wi, int lane, int* status) {
+__device__ __noinline__ int stage_collision(double* ws, int* wi, int lane, int* status) {
   const DevModel& m = c_m; const Layout& L = c_L;
   const double *gpos = ws + L.gpos, *gmat = ws + L.gmat;
   int* cand = wi + L.i_cand;

@@ -37,7 +37,7 @@ __device__ __forceinline__ void impedance(const double* solref, const double* so
 }
 
 // V_b = sum over the dofs on the path world -> b of cdof_d x_d
-__device__ __forceinline__ void body_vel(double* ws, const double* x, int lane) {
+__device__ __noinline__ void body_vel(double* ws, const double* x, int lane) {
   const DevModel& m = c_m; const Layout& L = c_L;
   const double* cdof = ws + L.cdof;
   double* Vb = ws + L.Vb;
@@ -52,7 +52,7 @@ __device__ __forceinline__ void body_vel(double* ws, const double* x, int lane) 
   __syncwarp();
 }
 // base rows of every contact applied to the current V_b: out slot `slot` (offset inside the contact record)
-__device__ __forceinline__ void contact_base(double* ws, const int* wi, int ncon, int slot, int lane) {
+__device__ __noinline__ void contact_base(double* ws, const int* wi, int ncon, int slot, int lane) {
   const Layout& L = c_L;
   const double* Vb = ws + L.Vb;
   LANE_LOOP(i, ncon) {
@@ -64,7 +64,7 @@ __device__ __forceinline__ void contact_base(double* ws, const int* wi, int ncon
     for (int k = 0; k < dim; k++) c[slot + k] = k < 3 ? v3dot(c + C_FRAME + 3 * k, pv) : v3dot(c + C_FRAME + 3 * (k - 3), rel);
   }
 }
-__device__ __forceinline__ void simple_base(double* ws, const int* wi, int nsr, const double* x, int field, int lane) {
+__device__ __noinline__ void simple_base(double* ws, const int* wi, int nsr, const double* x, int field, int lane) {
   const Layout& L = c_L;
   LANE_LOOP(i, nsr) {
     int A = wi[L.i_srA + i], B = wi[L.i_srB + i];
@@ -73,7 +73,7 @@ __device__ __forceinline__ void simple_base(double* ws, const int* wi, int nsr, 
 }
 
 // equality + limit rows and the velocity-dependent part of every row's reference acceleration.  Returns #simple rows.
-__device__ __forceinline__ int stage_constraints(double* ws, int* wi, int lane, int ncon, int* status) {
+__device__ __noinline__ int stage_constraints(double* ws, int* wi, int lane, int ncon, int* status) {
   const DevModel& m = c_m; const Layout& L = c_L;
   const double *qpos = ws + L.qpos, *qvel = ws + L.qvel;
   int nsr = 0;
@@ -152,7 +152,7 @@ struct RowIter {
 };
 
 // forces / active sets / constraint cost at the current ja; writes base forces into the jv slots and qfrc_constraint
-__device__ __forceinline__ double nt_update(double* ws, int* wi, int ncon, int nsr, int lane) {
+__device__ __noinline__ double nt_update(double* ws, int* wi, int ncon, int nsr, int lane) {
   const DevModel& m = c_m; const Layout& L = c_L;
   double cost = 0;
   const int ja = c_ja(), jv = c_jv();
@@ -221,7 +221,7 @@ __device__ __forceinline__ double nt_update(double* ws, int* wi, int ncon, int n
 }
 
 // constraint cost only (used for the warm-start choice); base values taken from slot `slot` / simple-row field `field`
-__device__ __forceinline__ double rows_cost(double* ws, const int* wi, int ncon, int nsr, int slot, int field, int lane) {
+__device__ __noinline__ double rows_cost(double* ws, const int* wi, int ncon, int nsr, int slot, int field, int lane) {
   const Layout& L = c_L;
   double cost = 0;
   LANE_LOOP(i, ncon) {
@@ -236,132 +236,12 @@ __device__ __forceinline__ double rows_cost(double* ws, const int* wi, int ncon,
   return warp_sum(cost);
 }
 
-#define HIDX(i, j) (((i) * ((i) + 1)) / 2 + (j))
-
-// H = M + J^T D_act J  (packed lower triangle) with its row envelope first[i]
-__device__ __forceinline__ void build_hessian(double* ws, int* wi, int ncon, int nsr, int lane) {
-  const DevModel& m = c_m; const Layout& L = c_L;
-  double* H = ws + L.H;
-  const double *qM = ws + L.qM, *cdof = ws + L.cdof;
-  int* first = wi + L.i_first;
-  int nH = m.nv * (m.nv + 1) / 2;
-  LANE_LOOP(i, nH) H[i] = 0;
-  __syncwarp();
-  LANE_LOOP(i, m.nv) {
-    int a = m.dof_Madr[i], k = 0, j = i, root = i;
-    for (; j >= 0; j = m.dof_parentid[j], k++) { H[HIDX(i, j)] = qM[a + k]; root = j; }
-    first[i] = root;
-  }
-  __syncwarp();
-  for (int ci = 0; ci < ncon; ci++) {
-    const double* c = ws + L.con + ci * L.cstride;
-    int mask = wi[L.i_cact + ci];
-    if (!mask) continue;
-    int dim = wi[L.i_cdim + ci], b1 = wi[L.i_cb1 + ci], b2 = wi[L.i_cb2 + ci];
-    // dof list of the two chains without their common ancestors (whose Jacobian entries cancel exactly)
-    int i1 = m.body_lastdof[b1], i2 = m.body_lastdof[b2], n = 0, mydof = -1, minE = 0x7fffffff;
-    double mysgn = 0;
-    while (i1 != i2) {
-      int e; double s;
-      if (i2 > i1) { e = i2; s = 1.0; i2 = m.dof_parentid[i2]; } else { e = i1; s = -1.0; i1 = m.dof_parentid[i1]; }
-      if (n == lane) { mydof = e; mysgn = s; }
-      if (e < minE) minE = e;
-      n++;
-    }
-    // active-set weights: W00 = D*nact, W0k = D*mu_k*(a+ - a-), Wkk = D*mu_k^2*(a+ + a-)
-    double D = c[C_D], J[6] = {0, 0, 0, 0, 0, 0}, t[6];
-    if (lane < n) {
-      const double* cd = cdof + 6 * mydof;
-      double pu[3];
-      for (int k = 0; k < dim; k++) {
-        if (k < 3) { v3cross(pu, c + C_POS, c + C_FRAME + 3 * k); J[k] = mysgn * (v3dot(c + C_FRAME + 3 * k, cd + 3) + v3dot(pu, cd)); }
-        else J[k] = mysgn * v3dot(c + C_FRAME + 3 * (k - 3), cd);
-      }
-      if (first[mydof] > minE) first[mydof] = minE;
-    }
-    if (dim == 1) { t[0] = D * J[0]; }
-    else {
-      int nact = __popc(mask);
-      double t0 = nact * J[0];
-      for (int k = 1; k < dim; k++) {
-        int ap = (mask >> (2 * (k - 1))) & 1, an = (mask >> (2 * (k - 1) + 1)) & 1;
-        double mu = c[C_MU + k - 1];
-        t0 += mu * (ap - an) * J[k];
-        t[k] = D * mu * ((ap - an) * J[0] + mu * (ap + an) * J[k]);
-      }
-      t[0] = D * t0;
-    }
-    for (int j = 0; j < n; j++) {
-      int dj = __shfl_sync(FULL, mydof, j);
-      double h = 0;
-      for (int k = 0; k < dim; k++) h += t[k] * __shfl_sync(FULL, J[k], j);
-      if (lane < n && mydof >= dj) H[HIDX(mydof, dj)] += h;
-    }
-    __syncwarp();
-  }
-  if (lane == 0)
-    for (int i = 0; i < nsr; i++) {
-      if (!wi[L.i_sract + i]) continue;
-      int A = wi[L.i_srA + i], B = wi[L.i_srB + i];
-      double D = srv(ws, SR_D, i), ca = srv(ws, SR_CA, i), cb = srv(ws, SR_CB, i);
-      H[HIDX(A, A)] += D * ca * ca;
-      if (B >= 0) {
-        H[HIDX(B, B)] += D * cb * cb;
-        int hi = A > B ? A : B, lo = A > B ? B : A;
-        H[HIDX(hi, lo)] += D * ca * cb;
-        if (first[hi] > lo) first[hi] = lo;
-      }
-    }
-  __syncwarp();
-}
-
-// in-place skyline Cholesky H = L L^T (right-looking; each lane owns rows lane, lane+32, ...), then x := -H^-1 g
-__device__ __forceinline__ void cholesky_solve(double* ws, const int* wi, double* x, const double* g, int lane) {
-  const DevModel& m = c_m; const Layout& L = c_L;
-  double* H = ws + L.H;
-  const int* first = wi + L.i_first;
-  int nv = m.nv;
-  for (int j = 0; j < nv; j++) {
-    double d = H[HIDX(j, j)];
-    if (d < GE_MINVAL) d = GE_MINVAL;
-    double ljj = sqrt(d), inv = 1.0 / ljj;
-    __syncwarp();
-    for (int i = j + 1 + lane; i < nv; i += 32)
-      if (first[i] <= j) H[HIDX(i, j)] *= inv;
-    if (lane == 0) H[HIDX(j, j)] = ljj;
-    __syncwarp();
-    for (int i = j + 1 + lane; i < nv; i += 32) {
-      if (first[i] > j) continue;
-      double lij = H[HIDX(i, j)];
-      if (lij == 0.0) continue;
-      for (int k = j + 1; k <= i; k++)
-        if (first[k] <= j) H[HIDX(i, k)] -= lij * H[HIDX(k, j)];
-    }
-    __syncwarp();
-  }
-  LANE_LOOP(i, nv) x[i] = g[i];
-  __syncwarp();
-  for (int j = 0; j < nv; j++) {  // L y = g, column oriented
-    double yj = x[j] / H[HIDX(j, j)];
-    __syncwarp();
-    if (lane == 0) x[j] = yj;
-    for (int i = j + 1 + lane; i < nv; i += 32)
-      if (first[i] <= j) x[i] -= H[HIDX(i, j)] * yj;
-    __syncwarp();
-  }
-  for (int i = nv - 1; i >= 0; i--) {  // L^T x = y, column oriented
-    double xi = x[i] / H[HIDX(i, i)];
-    __syncwarp();
-    if (lane == 0) x[i] = xi;
-    for (int k = first[i] + lane; k < i; k += 32) x[k] -= H[HIDX(i, k)] * xi;
-    __syncwarp();
-  }
-  LANE_LOOP(i, nv) x[i] = -x[i];
-  __syncwarp();
-}
+}  // namespace ge
+#include "ge_hessian.cuh"
+namespace ge {
 
 // Newton solver; returns the number of iterations. Output: ws[qacc], ws[qfrc_constraint].
-__device__ __forceinline__ int solve_newton(double* ws, int* wi, int lane, int ncon, int nsr) {
+__device__ __noinline__ int solve_newton(double* ws, int* wi, int lane, int ncon, int nsr) {
   const DevModel& m = c_m; const Layout& L = c_L;
   int nv = m.nv;
   double *qacc = ws + L.qacc, *qacc_smooth = ws + L.qacc_smooth, *qfrc_smooth = ws + L.qfrc_smooth, *qaccws = ws + L.qaccws;

@@ -15,7 +15,7 @@ namespace ge {
 struct StepInfo { int ncon, nsr, niter; };
 
 // mj_forward: kinematics -> bias -> mass matrix -> collision -> constraints -> smooth acceleration -> Newton
-__device__ __forceinline__ StepInfo forward(double* ws, int* wi, int lane, int* status) {
+__device__ __noinline__ StepInfo forward(double* ws, int* wi, int lane, int* status) {
   const DevModel& m = c_m; const Layout& L = c_L;
   StepInfo si;
   stage_fk(ws, lane);
@@ -48,7 +48,7 @@ __device__ __forceinline__ StepInfo forward(double* ws, int* wi, int lane, int* 
 }
 
 // mj_step = mj_forward + semi-implicit Euler with implicit joint damping
-__device__ __forceinline__ StepInfo sim_step(double* ws, int* wi, int lane, int* status) {
+__device__ __noinline__ StepInfo sim_step(double* ws, int* wi, int lane, int* status) {
   const DevModel& m = c_m; const Layout& L = c_L;
   StepInfo si = forward(ws, wi, lane, status);
   double h = m.timestep;
@@ -83,7 +83,7 @@ __device__ __forceinline__ StepInfo sim_step(double* ws, int* wi, int lane, int*
 }
 
 // 7 PID controllers (Ki = 0), derivative on measurement with the fixed controller period dt_pid
-__device__ __forceinline__ double pid_and_delta(double* ws, int lane, int group_mask, double dt_pid) {
+__device__ __noinline__ double pid_and_delta(double* ws, int lane, int group_mask, double dt_pid) {
   const DevModel& m = c_m; const Layout& L = c_L;
   double* ctl = ws + L.ctl;
   double delta = 0;
@@ -101,7 +101,7 @@ __device__ __forceinline__ double pid_and_delta(double* ws, int lane, int group_
 }
 
 // analytic tool-down IK of the ur5_gripper.urdf chain; base = world position of base_link
-__device__ __forceinline__ bool ik_solve(const double* ee_pos, const double* base, double* q5) {
+__device__ __noinline__ bool ik_solve(const double* ee_pos, const double* base, double* q5) {
   const DevModel& m = c_m;
   const double* ch = m.ik_chain;
   double d1 = ch[0], d4 = ch[1], a1 = ch[2], a2 = ch[3], d5 = ch[4], d6 = ch[5], p[3];
@@ -141,13 +141,13 @@ struct Prog {
 enum { PH_NONE = 0, PH_PRE = 1, PH_PRE_CENTRE = 2, PH_ROTATE = 3, PH_OPEN_HALF = 4, PH_DESCEND = 5, PH_STAY1 = 6, PH_CLOSE = 7,
        PH_CENTRE = 8, PH_DROP = 9, PH_CHECK = 10, PH_OPEN = 11, PH_STAY2 = 12, PH_ROTATE_BACK = 13, PH_STAY_ONLY = 20 };
 
-__device__ __forceinline__ void start_group(Cmd& c, double* ws, int lane, int mask, const double* target, double tol, int maxsteps) {
+__device__ __noinline__ void start_group(Cmd& c, double* ws, int lane, int mask, const double* target, double tol, int maxsteps) {
   const Layout& L = c_L;
   if (target && lane == 0) { int k = 0; for (int i = 0; i < GE_NU; i++) if (mask >> i & 1) ws[L.ctl + CTL_TARGET + i] = target[k++]; }
   __syncwarp();
   c.active = 1; c.mask = mask; c.tol = tol; c.maxsteps = maxsteps; c.steps = 1; c.result = 0; c.reached = 0;
 }
-__device__ __forceinline__ void start_ee(Cmd& c, double* ws, int lane, const double* xyz, const double* base, double tol, int maxsteps) {
+__device__ __noinline__ void start_ee(Cmd& c, double* ws, int lane, const double* xyz, const double* base, double tol, int maxsteps) {
   double q5[5];
   if (!ik_solve(xyz, base, q5)) { c.active = 0; c.result = 3; c.steps = 0; return; }
   start_group(c, ws, lane, 0x1f, q5, tol, maxsteps);
@@ -155,7 +155,7 @@ __device__ __forceinline__ void start_ee(Cmd& c, double* ws, int lane, const dou
 
 // Called when the current movement has ended; starts the next movement of the grasp program (if any).
 // info[12] mirrors the oracle's per-phase record.  Returns false when the program is finished.
-__device__ __forceinline__ bool prog_advance(Prog& p, Cmd& c, double* ws, int lane, const double* base, int* info, unsigned char* reward) {
+__device__ __noinline__ bool prog_advance(Prog& p, Cmd& c, double* ws, int lane, const double* base, int* info, unsigned char* reward) {
   const Layout& L = c_L;
   const double centre[3] = {0.0, -0.6, 1.1}, drop[3] = {0.6, 0.0, 1.15};
   const double ROT_DEG[6] = {0, 30, 60, 90, -30, -60};

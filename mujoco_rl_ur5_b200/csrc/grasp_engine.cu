@@ -26,47 +26,60 @@ extern "C" const char* ge_version(void) { return "grasp_engine 0.1 sm_100a fp64 
 // ------------------------------------------------------------------------------------------------ kernels
 // Sub-step kernel: one warp per environment.  Loads the env's state rows into its shared-memory slice, runs up to `nsub`
 // iterations of the reference control loop (PID -> mj_step) including movement / grasp-program transitions, writes back.
-__global__ void __launch_bounds__(32) k_run(EnvArrays E, int n_env, int nsub, double base_x, double base_y, double base_z) {
+// A CTA holds `blockDim.y` warps (= environments); they meet at one barrier per sub-step so that the warps of an SM walk the
+// (large) sub-step code roughly together and share instruction-cache lines.
+__global__ void __launch_bounds__(256) k_run(EnvArrays E, int n_env, int nsub, double base_x, double base_y, double base_z) {
   extern __shared__ double smem[];
   const DevModel& m = c_m; const Layout& L = c_L;
-  int env = blockIdx.x, lane = threadIdx.x;
-  if (env >= n_env) return;
+  int env = blockIdx.x * blockDim.y + threadIdx.y, lane = threadIdx.x;
+  bool valid = env < n_env;
   Cmd c;
-  c.active = E.cmd_active[env];
+  c.active = valid ? E.cmd_active[env] : 0;
   Prog p;
-  p.phase = E.prog_phase[env];
-  if (!c.active && p.phase == PH_NONE) return;
-  double* ws = smem;
-  int* wi = (int*)(smem + L.total_doubles);
-  c.mask = E.cmd_mask[env]; c.maxsteps = E.cmd_maxsteps[env]; c.steps = E.cmd_steps[env]; c.result = E.cmd_result[env]; c.tol = E.cmd_tol[env];
-  c.reached = 0;
-  p.rot = E.prog_rot[env]; p.grasp = E.prog_grasp[env]; p.aux = E.prog_aux[env] & 0xffff; p.r1 = (E.prog_aux[env] >> 16) & 0xf; p.rfinal = ((E.prog_aux[env] >> 20) & 0xf) - 1;
-  for (int k = 0; k < 3; k++) p.coords[k] = E.prog_coords[3 * env + k];
-  p.table = E.prog_table[env];
+  p.phase = valid ? E.prog_phase[env] : PH_NONE;
+  bool busy = c.active || p.phase != PH_NONE;
+  if (!__syncthreads_or(busy)) return;
+  double* ws = smem + (size_t)threadIdx.y * (L.total_bytes / 8);
+  int* wi = (int*)(ws + L.total_doubles);
   int info[12];
-  for (int k = 0; k < 12; k++) info[k] = E.prog_info[12 * env + k];
-  unsigned char reward = E.reward[env];
-  int status = E.status[env];
+  unsigned char reward = 0;
+  int status = 0;
   long long nstep = 0;
-  LANE_LOOP(i, m.nq) ws[L.qpos + i] = E.qpos[(size_t)env * m.nq + i];
-  LANE_LOOP(i, m.nv) { ws[L.qvel + i] = E.qvel[(size_t)env * m.nv + i]; ws[L.qaccws + i] = E.qaccws[(size_t)env * m.nv + i]; }
-  ws[L.ctl + lane] = E.ctl[(size_t)env * 32 + lane];
-  __syncwarp();
-  const double base[3] = {base_x, base_y, base_z};
-  int it = 0;
-  while (it < nsub) {
-    if (!c.active) {
-      if (p.phase == PH_NONE) break;
-      if (!prog_advance(p, c, ws, lane, base, info, &reward)) break;
-      continue;
-    }
-    double delta = pid_and_delta(ws, lane, c.mask, m.timestep);
-    if (delta < c.tol) { c.result = 1; c.reached = 1; }
-    if (c.steps > c.maxsteps) { c.result = 2; c.active = 0; continue; }
-    sim_step(ws, wi, lane, &status);
-    c.steps++; it++; nstep++;
-    if (c.reached) c.active = 0;
+  c.reached = 0;
+  if (busy) {
+    c.mask = E.cmd_mask[env]; c.maxsteps = E.cmd_maxsteps[env]; c.steps = E.cmd_steps[env]; c.result = E.cmd_result[env]; c.tol = E.cmd_tol[env];
+    p.rot = E.prog_rot[env]; p.grasp = E.prog_grasp[env]; p.aux = E.prog_aux[env] & 0xffff; p.r1 = (E.prog_aux[env] >> 16) & 0xf; p.rfinal = ((E.prog_aux[env] >> 20) & 0xf) - 1;
+    for (int k = 0; k < 3; k++) p.coords[k] = E.prog_coords[3 * env + k];
+    p.table = E.prog_table[env];
+    for (int k = 0; k < 12; k++) info[k] = E.prog_info[12 * env + k];
+    reward = E.reward[env];
+    status = E.status[env];
+    LANE_LOOP(i, m.nq) ws[L.qpos + i] = E.qpos[(size_t)env * m.nq + i];
+    LANE_LOOP(i, m.nv) { ws[L.qvel + i] = E.qvel[(size_t)env * m.nv + i]; ws[L.qaccws + i] = E.qaccws[(size_t)env * m.nv + i]; }
+    ws[L.ctl + lane] = E.ctl[(size_t)env * 32 + lane];
+    __syncwarp();
   }
+  const double base[3] = {base_x, base_y, base_z};
+  bool running = busy;
+  for (int it = 0; it < nsub; it++) {
+    if (!__syncthreads_or(running)) break;
+    if (!running) continue;
+    // one iteration of the reference loop that ends in a physics step (or the env going idle)
+    while (true) {
+      if (!c.active) {
+        if (p.phase == PH_NONE || !prog_advance(p, c, ws, lane, base, info, &reward)) { running = false; break; }
+        continue;
+      }
+      double delta = pid_and_delta(ws, lane, c.mask, m.timestep);
+      if (delta < c.tol) { c.result = 1; c.reached = 1; }
+      if (c.steps > c.maxsteps) { c.result = 2; c.active = 0; continue; }
+      sim_step(ws, wi, lane, &status);
+      c.steps++; nstep++;
+      if (c.reached) c.active = 0;
+      break;
+    }
+  }
+  if (!busy) return;
   // a movement that just ended inside the last iteration still has to hand over to the program (no sub-step involved)
   while (!c.active && p.phase != PH_NONE) { if (!prog_advance(p, c, ws, lane, base, info, &reward)) break; }
   LANE_LOOP(i, m.nq) E.qpos[(size_t)env * m.nq + i] = ws[L.qpos + i];
@@ -225,6 +238,7 @@ struct ge_engine {
   std::vector<char> hblob;
   double base_pos[3];
   int64_t launches, substep_launches;
+  int wpb;           // warps (= envs) per CTA of the sub-step kernel
   int* d_nout; double* d_dbg;
   RenderCtx rctx;
 };
@@ -287,7 +301,7 @@ static void make_layout(const DevModel& m, Layout& L) {
   auto takeI = [&](int n) { int r = io; io += n; return r; };
   L.i_cb1 = takeI(GE_MAXCON); L.i_cb2 = takeI(GE_MAXCON); L.i_cdim = takeI(GE_MAXCON); L.i_cpair = takeI(GE_MAXCON); L.i_cact = takeI(GE_MAXCON);
   L.i_srA = takeI(GE_MAXSR); L.i_srB = takeI(GE_MAXSR); L.i_srtype = takeI(GE_MAXSR); L.i_sract = takeI(GE_MAXSR);
-  L.i_cand = takeI(GE_MAXCAND); L.i_first = takeI(nv); L.i_misc = takeI(8);
+  L.i_cand = takeI(GE_MAXCAND); L.i_first = takeI(nv); L.i_tcoupled = takeI(m.ntree); L.i_misc = takeI(8);
   L.total_ints = align_up(io, 4);
   L.total_bytes = L.total_doubles * 8 + L.total_ints * 4;
 }
@@ -322,7 +336,7 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
   m.jnt_type = PI("jnt_type"); m.jnt_bodyid = PI("jnt_bodyid"); m.jnt_qposadr = PI("jnt_qposadr"); m.jnt_dofadr = PI("jnt_dofadr"); m.jnt_limited = PI("jnt_limited");
   m.jnt_pos = PD("jnt_pos"); m.jnt_axis = PD("jnt_axis"); m.jnt_range = PD("jnt_range"); m.jnt_margin = PD("jnt_margin"); m.jnt_solref = PD("jnt_solref"); m.jnt_solimp = PD("jnt_solimp");
   m.dof_bodyid = PI("dof_bodyid"); m.dof_jntid = PI("dof_jntid"); m.dof_parentid = PI("dof_parentid"); m.dof_Madr = PI("dof_Madr");
-  m.dof_subtreenum = PI("dof_subtreenum"); m.dof_depth = PI("dof_depth"); m.tree_dofadr = PI("tree_dofadr"); m.tree_dofnum = PI("tree_dofnum");
+  m.dof_subtreenum = PI("dof_subtreenum"); m.dof_depth = PI("dof_depth"); m.dof_treeindex = PI("dof_treeindex"); m.tree_dofadr = PI("tree_dofadr"); m.tree_dofnum = PI("tree_dofnum");
   m.dof_armature = PD("dof_armature"); m.dof_damping = PD("dof_damping"); m.dof_invweight0 = PD("dof_invweight0");
   m.geom_type = PI("geom_type"); m.geom_bodyid = PI("geom_bodyid"); m.geom_meshid = PI("geom_meshid");
   m.geom_pos = PD("geom_pos"); m.geom_lmat = PD("geom_lmat"); m.geom_size = PD("geom_size"); m.geom_rbound = PD("geom_rbound");
@@ -353,8 +367,12 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
   make_layout(m, h->lay);
   CK(cudaMemcpyToSymbol(c_m, &m, sizeof m));
   CK(cudaMemcpyToSymbol(c_L, &h->lay, sizeof(Layout)));
+  h->wpb = 2;  // measured best on B200 (r01: 1/2/4/7 warps per CTA -> 1.23/1.42/0.99/1.26 M sub-steps/s)
+  if (h->wpb * h->lay.total_bytes > 227 * 1024) h->wpb = 1;
+  if (const char* ev = getenv("GE_WPB")) { int v = atoi(ev); if (v >= 1 && v <= 8 && v * h->lay.total_bytes <= 227 * 1024) h->wpb = v; }
+  if (h->wpb < 1) { cudaFree(h->dblob); delete h; return fail(GE_ERR_MODEL, "model too large for the per-warp shared-memory workspace"); }
+  CK(cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, h->wpb * h->lay.total_bytes));
   if (h->lay.total_bytes > 48 * 1024) {
-    CK(cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, h->lay.total_bytes));
     CK(cudaFuncSetAttribute(k_debug, cudaFuncAttributeMaxDynamicSharedMemorySize, h->lay.total_bytes));
     CK(cudaFuncSetAttribute(k_body_xpos, cudaFuncAttributeMaxDynamicSharedMemorySize, h->lay.total_bytes));
   }
@@ -476,7 +494,9 @@ extern "C" int ge_grasp(ge_handle h, const double* coords, const int32_t* rot, d
 extern "C" int ge_run_async(ge_handle h, int substeps) {
   if (!h || substeps <= 0) return fail(GE_ERR_ARG, "ge_run_async: bad argument");
   if (bind(h)) return GE_ERR_CUDA;
-  k_run<<<h->n_envs, 32, h->lay.total_bytes, h->stream>>>(h->E, h->n_envs, substeps, h->base_pos[0], h->base_pos[1], h->base_pos[2]);
+  dim3 blk(32, h->wpb);
+  k_run<<<(h->n_envs + h->wpb - 1) / h->wpb, blk, (size_t)h->wpb * h->lay.total_bytes, h->stream>>>(h->E, h->n_envs, substeps, h->base_pos[0], h->base_pos[1],
+                                                                                                   h->base_pos[2]);
   h->launches++; h->substep_launches++;
   CK(cudaGetLastError());
   return GE_OK;

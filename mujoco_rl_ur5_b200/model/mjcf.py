@@ -461,6 +461,7 @@ def compile_mjcf(path):
     M["body_subtreenum"] = body_subtreenum
     M["dof_subtreenum"] = dof_subtreenum
     M["dof_depth"] = dof_depth
+    M["dof_treeindex"] = np.array([tree_roots.index(int(dof_tree[d])) for d in range(nv)], np.int32)
     M["tree_dofadr"] = np.array(tree_roots, np.int32)
     M["tree_dofnum"] = np.array([dof_subtreenum[d] for d in tree_roots], np.int32)
     M["ntree"] = len(tree_roots)
