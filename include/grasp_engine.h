@@ -53,6 +53,11 @@ int ge_get_body_xpos(ge_handle h, double* xpos);
 /* controller.actuators[i][4].Kp = value (GraspingEnv.py:282,347): kp [N] [dev] or NULL with scalar `value` for all envs */
 int ge_set_gain(ge_handle h, int actuator, const double* kp, double value);
 
+/* controller.current_target_joint_values / PID set-points for ALL 7 actuators (MujocoController.py:313-316): target [N,7] [dev] */
+int ge_set_targets(ge_handle h, const double* target);
+/* reads them back: target [N,7] [dev] */
+int ge_get_targets(ge_handle h, double* target);
+
 /* MJ_Controller.move_group_to_joint_target (MujocoController.py:269-393) set-up half: group_mask bit i = actuator i in
  * the group; target [N,7] [dev] (entries of non-members ignored; NULL = keep current targets); tolerance/max_steps scalars.
  * env_mask [N] u8 [dev] or NULL.  The movement runs inside ge_run. */

@@ -189,6 +189,13 @@ __global__ void k_command(EnvArrays E, int n_env, int kind, int mask, const doub
     E.cmd_active[env] = 1; E.cmd_mask[env] = 0x1f; E.cmd_tol[env] = 0.05; E.cmd_maxsteps[env] = 1000; E.cmd_steps[env] = 1; E.cmd_result[env] = 0;
   }
 }
+__global__ void k_targets(EnvArrays E, int n_env, const double* in, double* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_env * GE_NU) return;
+  int env = i / GE_NU, a = i % GE_NU;
+  if (in) E.ctl[(size_t)env * 32 + CTL_TARGET + a] = in[i];
+  if (out) out[i] = E.ctl[(size_t)env * 32 + CTL_TARGET + a];
+}
 __global__ void k_busy(EnvArrays E, int n_env, unsigned char* busy) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env < n_env) busy[env] = (E.cmd_active[env] || E.prog_phase[env] != PH_NONE) ? 1 : 0;
@@ -540,6 +547,22 @@ extern "C" int ge_get_status(ge_handle h, int32_t* status) {
   if (!h || !status) return GE_ERR_ARG;
   if (bind(h)) return GE_ERR_CUDA;
   CK(cudaMemcpyAsync(status, h->E.status, 4 * (size_t)h->n_envs, cudaMemcpyDeviceToDevice, h->stream));
+  return GE_OK;
+}
+extern "C" int ge_set_targets(ge_handle h, const double* target) {
+  if (!h || !target) return GE_ERR_ARG;
+  if (bind(h)) return GE_ERR_CUDA;
+  k_targets<<<(h->n_envs * GE_NU + 127) / 128, 128, 0, h->stream>>>(h->E, h->n_envs, target, nullptr);
+  h->launches++;
+  CK(cudaGetLastError());
+  return GE_OK;
+}
+extern "C" int ge_get_targets(ge_handle h, double* target) {
+  if (!h || !target) return GE_ERR_ARG;
+  if (bind(h)) return GE_ERR_CUDA;
+  k_targets<<<(h->n_envs * GE_NU + 127) / 128, 128, 0, h->stream>>>(h->E, h->n_envs, nullptr, target);
+  h->launches++;
+  CK(cudaGetLastError());
   return GE_OK;
 }
 extern "C" int ge_get_busy(ge_handle h, uint8_t* busy) {

@@ -15,7 +15,7 @@ _LIB = None
 
 SYMBOLS = [
     "ge_last_error", "ge_version", "ge_create", "ge_destroy", "ge_size", "ge_set_state", "ge_get_state", "ge_get_body_xpos",
-    "ge_set_gain", "ge_move_group", "ge_move_ee", "ge_stay", "ge_grasp", "ge_run", "ge_run_async", "ge_get_results",
+    "ge_set_gain", "ge_set_targets", "ge_get_targets", "ge_move_group", "ge_move_ee", "ge_stay", "ge_grasp", "ge_run", "ge_run_async", "ge_get_results",
     "ge_get_grasp_info", "ge_get_status", "ge_get_busy", "ge_ik", "ge_pixel_2_world", "ge_render", "ge_debug_forward", "ge_counters",
 ]
 GROUPS = {"All": 0x7F, "Arm": 0x1F, "Gripper": 0x40}
@@ -43,6 +43,8 @@ def load_library():
         L.ge_get_state.argtypes = [P, P, P]
         L.ge_get_body_xpos.argtypes = [P, P]
         L.ge_set_gain.argtypes = [P, C.c_int, P, C.c_double]
+        L.ge_set_targets.argtypes = [P, P]
+        L.ge_get_targets.argtypes = [P, P]
         L.ge_move_group.argtypes = [P, C.c_int, P, C.c_double, C.c_int, P]
         L.ge_move_ee.argtypes = [P, P, C.c_double, C.c_int, P]
         L.ge_stay.argtypes = [P, C.c_int, P]
@@ -143,6 +145,18 @@ class BatchedEngine:
             kp = self._dev(value, t.float64)
             self._ck(self.L.ge_set_gain(self.h, actuator, _ptr(kp), 0.0), "ge_set_gain")
             self._keep = kp
+
+    def set_targets(self, target):
+        t = self.torch
+        tg = self._dev(target, t.float64).reshape(self.n_envs, 7)
+        self._ck(self.L.ge_set_targets(self.h, _ptr(tg)), "ge_set_targets")
+        self._keep = tg
+
+    def get_targets(self):
+        t = self.torch
+        tg = t.empty((self.n_envs, 7), dtype=t.float64, device=self.device)
+        self._ck(self.L.ge_get_targets(self.h, _ptr(tg)), "ge_get_targets")
+        return tg
 
     # ------------------------------------------------------------------ movements
     def move_group(self, group="All", target=None, tolerance=0.1, max_steps=10000, env_mask=None):

@@ -1,0 +1,75 @@
+"""The reference-facing façade on the GPU: `gym.make("gym_grasper:Grasper-v0")` -> GraspEnv / MJ_Controller, driven like
+example_agent.py (reference: example_agent.py:8-26) and checked against the oracle for one attempt."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+COMPAT = os.path.join(ROOT, "mujoco_rl_ur5_b200", "compat")
+
+
+@pytest.fixture(scope="module")
+def env():
+    sys.path.insert(0, COMPAT)
+    import gym
+
+    e = gym.make("gym_grasper:Grasper-v0", show_obs=False, render=False, quiet=True)
+    yield e
+    e.close()
+    sys.path.remove(COMPAT)
+
+
+def test_gym_surface(env):
+    assert list(env.action_space.nvec) == [40000, 6]
+    assert env.TABLE_HEIGHT == 0.91 and env.IMAGE_WIDTH == 200
+    cam = env.model.camera_name2id("top_down")
+    assert np.allclose(env.model.cam_pos0[cam], [0, -0.6, 2.0])
+    a = env.action_space.sample()
+    assert 0 <= a[0] < 40000 and 0 <= a[1] < 6
+    env.print_info()
+
+
+def test_reset_step_like_example_agent(env, scene_a):
+    from oracle.oracle_py import OracleEnv
+    from tests.common import object_positions
+
+    blob, A, _ = scene_a
+    np.random.seed(20)
+    obs = env.reset()
+    assert obs["rgb"].shape == (200, 200, 3) and obs["rgb"].dtype == np.uint8 and obs["depth"].shape == (200, 200)
+    assert float(obs["depth"].min()) < 1.09  # something (objects / arm) is above the table top, 1.09 m below the camera
+    q0 = env.data.qpos.copy()
+    v0 = env.data.qvel.copy()
+    # aim at the first box through the pixel interface
+    p = object_positions(A, q0)[0]
+    px, py = env.controller.world_2_pixel(np.array([p[0], p[1], p[2] + 0.02]))
+    obs2, reward, done, info = env.step([int(py) * 200 + int(px), 0])
+    assert reward in (0, 1) and done is False and obs2["depth"].shape == (200, 200)
+    # the same attempt on the oracle, from the same state, with the coordinates the env derived from its depth image
+    d = obs["depth"][int(py)][int(px)]
+    coords = env.controller.pixel_2_world(int(px), int(py), d)
+    o = OracleEnv(blob)
+    o.reset(q0, v0)
+    r, oinfo = o.move_and_grasp(coords, 0, 0.91)
+    assert r == reward and list(env.last_grasp_info) == oinfo
+    assert np.abs(env.data.qpos[:8] - o.qpos[:8]).max() < 1e-4
+    o.close()
+
+
+def test_controller_methods(env):
+    c = env.controller
+    assert c.groups["Arm"] == [0, 1, 2, 3, 4] and c.groups["Gripper"] == [6]
+    r = c.move_ee([0.0, -0.6, 1.1], max_steps=1000, tolerance=0.05, quiet=True)
+    assert r == "success" and c.last_steps > 1
+    r = c.open_gripper(quiet=True)
+    assert r == "success" or r.startswith("max")
+    r = c.move_ee([5.0, 5.0, 5.0], max_steps=10, quiet=True)
+    assert r.startswith("No")
+    c.actuators[0][4].Kp = 10.0
+    assert c.actuators[0][4].Kp == 10.0
+    c.stay(20)
+    xyz = c.pixel_2_world(136, 80, 1.11)
+    assert np.abs(xyz - [-0.16551974, -0.50804459, 0.88999999]).max() < 1e-6
