@@ -1474,3 +1474,18 @@ void orc_contact(Env* e, int i, double* out) {
   const Contact* c = &e->con[i];
   out[0] = c->dist; v3copy(out + 1, c->pos); memcpy(out + 4, c->frame, 72); out[13] = c->geom1; out[14] = c->geom2; out[15] = c->dim;
 }
+
+/* ------------------------------------------------------------------ camera math (MujocoController.py:729-806), pinned by tests/golden/camera_math.json */
+/* pixel_2_world: pos_w = R^-1 (K^-1 [x, y, 1] * (-depth) + cam_pos), K = [[f,0,W/2],[0,f,H/2],[0,0,1]], f = 0.5 H / tan(fovy pi/360) */
+void orc_pixel_2_world(const Model* m, int cam, int W, int H, double px, double py, double depth, double* out) {
+  double f = 0.5 * H / tan(m->cam_fovy[cam] * M_PI / 360.0), d = -depth;
+  double pc[3] = {(px * d - 0.5 * W * d) / f, (py * d - 0.5 * H * d) / f, d}, t[3];
+  v3add(t, pc, m->cam_pos0 + 3 * cam);
+  m3Tmulv(out, m->cam_mat0 + 9 * cam, t);
+}
+/* depth_2_meters: near / (1 - d (1 - near/far)), near = znear * extent, far = zfar * extent */
+double orc_depth_2_meters(const Model* m, double gl_depth) {
+  double near = m->znear * m->extent, far = m->zfar * m->extent;
+  return near / (1.0 - gl_depth * (1.0 - near / far));
+}
+Model* orc_env_model(Env* e) { return e->m; }

@@ -51,6 +51,9 @@ def lib():
         L.orc_ik.argtypes = [P, D, D]
         L.orc_move_ee.argtypes = [P, D, C.c_double, C.c_int, I]
         L.orc_move_and_grasp.argtypes = [P, D, C.c_int, C.c_double, I]
+        L.orc_pixel_2_world.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, D]
+        L.orc_depth_2_meters.restype = C.c_double
+        L.orc_depth_2_meters.argtypes = [P, C.c_double]
         L.orc_render.argtypes = [P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_float)]
         _LIB = L
     return _LIB
@@ -196,6 +199,14 @@ class OracleEnv:
         info = (C.c_int * 12)()
         r = self.L.orc_move_and_grasp(self.env, _dp(np.ascontiguousarray(coords, np.float64)), int(rot), table_height, info)
         return int(r), list(info)
+
+    def pixel_2_world(self, px, py, depth, cam=1, W=200, H=200):
+        out = np.zeros(3)
+        self.L.orc_pixel_2_world(self.model, cam, W, H, float(px), float(py), float(depth), _dp(out))
+        return out
+
+    def depth_2_meters(self, gl_depth):
+        return float(self.L.orc_depth_2_meters(self.model, float(gl_depth)))
 
     def render(self, cam=1, W=200, H=200):
         rgb = np.zeros((H, W, 3), np.uint8)
