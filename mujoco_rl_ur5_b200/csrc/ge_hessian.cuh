@@ -8,7 +8,7 @@
 #pragma once
 
 #define HIDX(i, j) (((i) * ((i) + 1)) / 2 + (j))
-#define GE_MAXE 16  // dofs of one contact after removing the common ancestors of the two chains
+#define GE_GROUP 8  // lanes per kinematic tree in the uncoupled-tree path (trees with more dofs use the coupled path)
 
 namespace ge {
 
@@ -44,14 +44,8 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
   double* H = ws + L.H;
   const double *qM = ws + L.qM, *cdof = ws + L.cdof;
   int *first = wi + L.i_first, *tcoupled = wi + L.i_tcoupled;
-  // ---- which trees are coupled to another tree by an active constraint
-  // GE_TREE_LOCAL=1 enables the one-lane-per-uncoupled-tree path.  Measured on B200 (r01): it halves throughput (a single
-  // lane walking a 6x6 block serially is latency-bound while 25 lanes idle), so the default treats every tree as coupled and
-  // uses the warp-cooperative path for all of them; the block structure still pays through the per-row envelopes.
-#ifndef GE_TREE_LOCAL
-#define GE_TREE_LOCAL 0
-#endif
-  LANE_LOOP(t, m.ntree) tcoupled[t] = GE_TREE_LOCAL ? 0 : 1;
+  // ---- which trees are coupled to another tree by an active constraint (trees wider than a lane group take the coupled path too)
+  LANE_LOOP(t, m.ntree) tcoupled[t] = m.tree_dofnum[t] > GE_GROUP ? 1 : 0;
   __syncwarp();
   LANE_LOOP(ci, ncon) {
     if (!wi[L.i_cact + ci]) continue;
@@ -73,46 +67,51 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
     first[i] = root;
   }
   __syncwarp();
-  // ---- uncoupled trees: one lane per tree adds the contacts (and simple rows) that live entirely inside its block
-  LANE_LOOP(t, m.ntree) {
-    if (tcoupled[t]) continue;
-    for (int ci = 0; ci < ncon; ci++) {
-      int mask = wi[L.i_cact + ci];
-      if (!mask) continue;
-      int b1 = wi[L.i_cb1 + ci], b2 = wi[L.i_cb2 + ci];
-      if (tree_of_body(b1) != t && tree_of_body(b2) != t) continue;
-      const double* c = ws + L.con + ci * L.cstride;
-      int dim = wi[L.i_cdim + ci];
-      int E[GE_MAXE];
-      double Jc[GE_MAXE][6], Tc[GE_MAXE][6];
-      int i1 = m.body_lastdof[b1], i2 = m.body_lastdof[b2], n = 0;
-      while (i1 != i2 && n < GE_MAXE) {
-        int e; double s;
-        if (i2 > i1) { e = i2; s = 1.0; i2 = m.dof_parentid[i2]; } else { e = i1; s = -1.0; i1 = m.dof_parentid[i1]; }
-        E[n] = e;
-        jac_column(c, dim, cdof + 6 * e, s, Jc[n]);
-        weight_column(c, dim, mask, Jc[n], Tc[n]);
-        n++;
-      }
-      for (int a = 0; a < n; a++)
-        for (int b = 0; b < n; b++) {
-          if (E[a] < E[b]) continue;
-          double h = 0;
-          for (int k = 0; k < dim; k++) h += Tc[a][k] * Jc[b][k];
-          H[HIDX(E[a], E[b])] += h;
+  // ---- uncoupled trees: one 8-lane group per tree (4 trees at a time); lane l of the group owns dof lo + l.
+  // For every active contact that lives inside the tree the group rebuilds its Jacobian block in registers and adds
+  // J^T W J to the tree's dense block with width-8 shuffles.  Groups run in lock-step but never touch each other's rows.
+  {
+    const int g = lane / GE_GROUP, l = lane % GE_GROUP;
+    const unsigned gmask = ((1u << GE_GROUP) - 1u) << (g * GE_GROUP);
+    for (int t0 = 0; t0 < m.ntree; t0 += 32 / GE_GROUP) {
+      int t = t0 + g;
+      if (t >= m.ntree || tcoupled[t]) continue;  // group-uniform
+      int lo = m.tree_dofadr[t], nt = m.tree_dofnum[t], mydof = l < nt ? lo + l : -1;
+      for (int ci = 0; ci < ncon; ci++) {
+        int mask = wi[L.i_cact + ci];
+        if (!mask) continue;
+        int b1 = wi[L.i_cb1 + ci], b2 = wi[L.i_cb2 + ci];
+        if (tree_of_body(b1) != t && tree_of_body(b2) != t) continue;
+        const double* c = ws + L.con + ci * L.cstride;
+        int dim = wi[L.i_cdim + ci];
+        // sign of my dof in the contact's dof list (chains of both bodies minus their common ancestors)
+        double sgn = 0;
+        int i1 = m.body_lastdof[b1], i2 = m.body_lastdof[b2];
+        while (i1 != i2) {
+          if (i2 > i1) { if (i2 == mydof) sgn = 1.0; i2 = m.dof_parentid[i2]; }
+          else { if (i1 == mydof) sgn = -1.0; i1 = m.dof_parentid[i1]; }
         }
-    }
-    for (int i = 0; i < nsr; i++) {
-      if (!wi[L.i_sract + i]) continue;
-      int A = wi[L.i_srA + i], B = wi[L.i_srB + i];
-      if (m.dof_treeindex[A] != t) continue;
-      double D = srv(ws, SR_D, i), ca = srv(ws, SR_CA, i), cb = srv(ws, SR_CB, i);
-      H[HIDX(A, A)] += D * ca * ca;
-      if (B >= 0) {
-        H[HIDX(B, B)] += D * cb * cb;
-        int hi = A > B ? A : B, lo = A > B ? B : A;
-        H[HIDX(hi, lo)] += D * ca * cb;
+        double J[6] = {0, 0, 0, 0, 0, 0}, tw[6] = {0, 0, 0, 0, 0, 0};
+        if (sgn != 0) { jac_column(c, dim, cdof + 6 * mydof, sgn, J); weight_column(c, dim, mask, J, tw); }
+        for (int f = 0; f < nt; f++) {
+          double h = 0;
+          for (int k = 0; k < dim; k++) h += tw[k] * __shfl_sync(gmask, J[k], f, GE_GROUP);
+          if (l >= f && l < nt && h != 0.0) H[HIDX(lo + l, lo + f)] += h;
+        }
       }
+      if (l == 0)
+        for (int i = 0; i < nsr; i++) {
+          if (!wi[L.i_sract + i]) continue;
+          int A = wi[L.i_srA + i], B = wi[L.i_srB + i];
+          if (m.dof_treeindex[A] != t) continue;
+          double D = srv(ws, SR_D, i), ca = srv(ws, SR_CA, i), cb = srv(ws, SR_CB, i);
+          H[HIDX(A, A)] += D * ca * ca;
+          if (B >= 0) {
+            H[HIDX(B, B)] += D * cb * cb;
+            int hi = A > B ? A : B, lw = A > B ? B : A;
+            H[HIDX(hi, lw)] += D * ca * cb;
+          }
+        }
     }
   }
   __syncwarp();
@@ -198,31 +197,49 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
 
 // x := -H^-1 g.  Uncoupled trees: dense left-looking Cholesky + substitutions, one lane per tree.  Coupled trees: skyline
 // right-looking Cholesky with the whole warp (each lane owns rows lane, lane+32, ...).
-__device__ __noinline__ void cholesky_solve(double* ws, const int* wi, double* x, const double* g, int lane) {
+__device__ __noinline__ void cholesky_solve(double* ws, const int* wi, double* x, const double* g_, int lane) {
   const DevModel& m = c_m; const Layout& L = c_L;
   double* H = ws + L.H;
   const int *first = wi + L.i_first, *tcoupled = wi + L.i_tcoupled;
   int nv = m.nv;
   bool any_coupled = false;
   for (int t = 0; t < m.ntree; t++) any_coupled |= tcoupled[t] != 0;
-  LANE_LOOP(t, m.ntree) {
-    if (tcoupled[t]) continue;
-    int lo = m.tree_dofadr[t], hi = lo + m.tree_dofnum[t];
-    for (int j = lo; j < hi; j++) {
-      double s = H[HIDX(j, j)];
-      for (int k = lo; k < j; k++) { double l = H[HIDX(j, k)]; s -= l * l; }
-      if (s < GE_MINVAL) s = GE_MINVAL;
-      double ljj = sqrt(s), inv = 1.0 / ljj;
-      H[HIDX(j, j)] = ljj;
-      for (int i = j + 1; i < hi; i++) {
-        double tt = H[HIDX(i, j)];
-        for (int k = lo; k < j; k++) tt -= H[HIDX(i, k)] * H[HIDX(j, k)];
-        H[HIDX(i, j)] = tt * inv;
+  {
+    // uncoupled trees: right-looking Cholesky + substitutions inside an 8-lane group, lane l owns row lo + l
+    const int g = lane / GE_GROUP, l = lane % GE_GROUP;
+    const unsigned gmask = ((1u << GE_GROUP) - 1u) << (g * GE_GROUP);
+    for (int t0 = 0; t0 < m.ntree; t0 += 32 / GE_GROUP) {
+      int t = t0 + g;
+      if (t >= m.ntree || tcoupled[t]) continue;  // group-uniform
+      int lo = m.tree_dofadr[t], nt = m.tree_dofnum[t], row = lo + l;
+      bool mine = l < nt;
+      for (int j = 0; j < nt; j++) {
+        double d = H[HIDX(lo + j, lo + j)];
+        if (d < GE_MINVAL) d = GE_MINVAL;
+        double ljj = sqrt(d), inv = 1.0 / ljj;
+        __syncwarp(gmask);
+        if (mine && l > j) H[HIDX(row, lo + j)] *= inv;
+        if (l == j) H[HIDX(row, row)] = ljj;
+        __syncwarp(gmask);
+        if (mine && l > j) {
+          double lij = H[HIDX(row, lo + j)];
+          for (int k = j + 1; k <= l; k++) H[HIDX(row, lo + k)] -= lij * H[HIDX(lo + k, lo + j)];
+        }
+        __syncwarp(gmask);
       }
+      double y = mine ? g_[row] : 0.0;  // L y = g (column oriented): after column j every later row subtracts L[row][j] y_j
+      for (int j = 0; j < nt; j++) {
+        double yj = __shfl_sync(gmask, y, j, GE_GROUP) / H[HIDX(lo + j, lo + j)];
+        if (l == j) y = yj;
+        else if (mine && l > j) y -= H[HIDX(row, lo + j)] * yj;
+      }
+      for (int i = nt - 1; i >= 0; i--) {  // L^T x = y
+        double xi = __shfl_sync(gmask, y, i, GE_GROUP) / H[HIDX(lo + i, lo + i)];
+        if (l == i) y = xi;
+        else if (mine && l < i) y -= H[HIDX(lo + i, row)] * xi;
+      }
+      if (mine) x[row] = -y;
     }
-    for (int i = lo; i < hi; i++) { double y = g[i]; for (int k = lo; k < i; k++) y -= H[HIDX(i, k)] * x[k]; x[i] = y / H[HIDX(i, i)]; }
-    for (int i = hi - 1; i >= lo; i--) { double y = x[i]; for (int k = i + 1; k < hi; k++) y -= H[HIDX(k, i)] * x[k]; x[i] = y / H[HIDX(i, i)]; }
-    for (int i = lo; i < hi; i++) x[i] = -x[i];
   }
   __syncwarp();
   if (!any_coupled) return;
@@ -245,7 +262,7 @@ __device__ __noinline__ void cholesky_solve(double* ws, const int* wi, double* x
     }
     __syncwarp();
   }
-  LANE_LOOP(i, nv) if (tcoupled[m.dof_treeindex[i]]) x[i] = g[i];
+  LANE_LOOP(i, nv) if (tcoupled[m.dof_treeindex[i]]) x[i] = g_[i];
   __syncwarp();
   for (int j = 0; j < nv; j++) {  // L y = g, column oriented
     if (!tcoupled[m.dof_treeindex[j]]) continue;

@@ -768,8 +768,10 @@ static int mpr_penetration(const Env* e, const Shape* A, const Shape* B, double*
   for (int k = 0; k < 3; k++) ppos[k] = 0.5 * (w[0] * (v1.a[k] + v1.b[k]) + w[1] * (v2.a[k] + v2.b[k]) + w[2] * (v3.a[k] + v3.b[k]));
   return 1;
 }
+long g_mpr_calls = 0, g_mpr_pairmask[64];
 static void col_convex(Env* e, int pair, int g1, int g2) {
   const Model* m = e->m;
+  g_mpr_calls++; g_mpr_pairmask[(g1 * 7 + g2) & 63]++;
   double margin = m->pair_margin[pair];
   Shape A = {e, g1, 0.5 * margin}, B = {e, g2, 0.5 * margin};
   double depth, dir[3], pos[3];
@@ -1489,3 +1491,5 @@ double orc_depth_2_meters(const Model* m, double gl_depth) {
   return near / (1.0 - gl_depth * (1.0 - near / far));
 }
 Model* orc_env_model(Env* e) { return e->m; }
+
+long orc_mpr_calls(void) { return g_mpr_calls; }
