@@ -14,8 +14,18 @@ namespace ge {
 
 struct StepInfo { int ncon, nsr, niter; };
 
+// Stage barriers: when GE_STAGE_SYNC is on, all warps of the CTA (one env each) enter collision, the constraint solver and the
+// integrator together, so that the SM's instruction cache serves the (large) stage code once per CTA instead of once per warp.
+// Warps that do not step in an iteration must call stage_barriers_idle() to keep the barrier counts equal.
+#ifndef GE_STAGE_SYNC
+#define GE_STAGE_SYNC 1
+#endif
+#define GE_NUM_STAGE_BARRIERS 3
+__device__ __forceinline__ void stage_barrier(bool sync) { if (GE_STAGE_SYNC && sync) __syncthreads(); }
+__device__ __forceinline__ void stage_barriers_idle() { if (GE_STAGE_SYNC) for (int k = 0; k < GE_NUM_STAGE_BARRIERS; k++) __syncthreads(); }
+
 // mj_forward: kinematics -> bias -> mass matrix -> collision -> constraints -> smooth acceleration -> Newton
-__device__ __noinline__ StepInfo forward(double* ws, int* wi, int lane, int* status) {
+__device__ __noinline__ StepInfo forward(double* ws, int* wi, int lane, int* status, bool sync = false) {
   const DevModel& m = c_m; const Layout& L = c_L;
   StepInfo si;
   stage_fk(ws, lane);
@@ -24,6 +34,7 @@ __device__ __noinline__ StepInfo forward(double* ws, int* wi, int lane, int* sta
   LANE_LOOP(i, m.nM) ws[L.qLD + i] = ws[L.qM + i];
   __syncwarp();
   factor_trees(ws + L.qLD, lane);
+  stage_barrier(sync);
   si.ncon = stage_collision(ws, wi, lane, status);
   // smooth forces: passive (joint damping) - bias + actuation (torque motors, gear * clamp(ctrl))
   const double *qvel = ws + L.qvel, *ctrl = ws + L.ctl + CTL_CTRL;
@@ -39,6 +50,7 @@ __device__ __noinline__ StepInfo forward(double* ws, int* wi, int lane, int* sta
   LANE_LOOP(d, m.nv) qas[d] = qfs[d];
   __syncwarp();
   solve_trees(ws + L.qLD, qas, lane);
+  stage_barrier(sync);
   si.nsr = stage_constraints(ws, wi, lane, si.ncon, status);
   si.niter = solve_newton(ws, wi, lane, si.ncon, si.nsr);
   if (si.niter >= m.iterations) *status |= 4;
@@ -48,9 +60,10 @@ __device__ __noinline__ StepInfo forward(double* ws, int* wi, int lane, int* sta
 }
 
 // mj_step = mj_forward + semi-implicit Euler with implicit joint damping
-__device__ __noinline__ StepInfo sim_step(double* ws, int* wi, int lane, int* status) {
+__device__ __noinline__ StepInfo sim_step(double* ws, int* wi, int lane, int* status, bool sync = false) {
   const DevModel& m = c_m; const Layout& L = c_L;
-  StepInfo si = forward(ws, wi, lane, status);
+  StepInfo si = forward(ws, wi, lane, status, sync);
+  stage_barrier(sync);
   double h = m.timestep;
   double *acc = ws + L.grad, *qH = ws + L.qLD, *qvel = ws + L.qvel, *qpos = ws + L.qpos;
   LANE_LOOP(d, m.nv) acc[d] = ws[L.qfrc_smooth + d] + ws[L.qfrc_constraint + d];

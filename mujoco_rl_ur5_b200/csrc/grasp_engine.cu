@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(256) k_run(EnvArrays E, int n_env, int nsub, d
   bool running = busy;
   for (int it = 0; it < nsub; it++) {
     if (!__syncthreads_or(running)) break;
-    if (!running) continue;
+    if (!running) { stage_barriers_idle(); continue; }
+    bool stepped = false;
     // one iteration of the reference loop that ends in a physics step (or the env going idle)
     while (true) {
       if (!c.active) {
@@ -73,11 +74,13 @@ __global__ void __launch_bounds__(256) k_run(EnvArrays E, int n_env, int nsub, d
       double delta = pid_and_delta(ws, lane, c.mask, m.timestep);
       if (delta < c.tol) { c.result = 1; c.reached = 1; }
       if (c.steps > c.maxsteps) { c.result = 2; c.active = 0; continue; }
-      sim_step(ws, wi, lane, &status);
+      sim_step(ws, wi, lane, &status, true);
+      stepped = true;
       c.steps++; nstep++;
       if (c.reached) c.active = 0;
       break;
     }
+    if (!stepped) stage_barriers_idle();
   }
   if (!busy) return;
   // a movement that just ended inside the last iteration still has to hand over to the program (no sub-step involved)
@@ -374,7 +377,8 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
   make_layout(m, h->lay);
   CK(cudaMemcpyToSymbol(c_m, &m, sizeof m));
   CK(cudaMemcpyToSymbol(c_L, &h->lay, sizeof(Layout)));
-  h->wpb = 2;  // measured best on B200 (r01: 1/2/4/7 warps per CTA -> 1.23/1.42/0.99/1.26 M sub-steps/s)
+  // warps (= envs) per CTA; measured on B200 with stage barriers: 2/3/4/7 -> 1.46/1.51/1.10/1.35 M sub-steps/s; GE_WPB overrides
+  h->wpb = 3;
   if (h->wpb * h->lay.total_bytes > 227 * 1024) h->wpb = 1;
   if (const char* ev = getenv("GE_WPB")) { int v = atoi(ev); if (v >= 1 && v <= 8 && v * h->lay.total_bytes <= 227 * 1024) h->wpb = v; }
   if (h->wpb < 1) { cudaFree(h->dblob); delete h; return fail(GE_ERR_MODEL, "model too large for the per-warp shared-memory workspace"); }
