@@ -1,0 +1,42 @@
+/* grasp_qnet.h — C-ABI of the batched pixel-wise grasp Q-network forward (libgrasp_qnet.so).
+ *
+ * Stands in for `policy_net(state)` in the reference agent (Grasping_Agent_multidiscrete.py:254,295) where
+ * policy_net = Modules.MULTIDISCRETE_RESNET(6) (Modules.py:308-311).  The layer functions below are the building blocks
+ * (one per nn.Module type the network uses); mujoco_rl_ur5_b200/qnet.py strings them together in the order of
+ * Perception_Module.forward (Modules.py:170-193) and Grasping_Module_multidiscrete.forward (:256-287).
+ * All pointers are CUDA device pointers; activations are NHWC bf16 unless stated; every call is asynchronous on `stream`
+ * (cudaStream_t cast to void*).  Return 0 on success, negative on error (gq_last_error()).
+ */
+#ifndef GRASP_QNET_H
+#define GRASP_QNET_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* gq_last_error(void);
+const char* gq_version(void);
+
+/* nn.Conv2d(Cin, Cout, kernel_size=ks, padding=ks/2, stride=1) for ks in {1,3}, Cin and Cout multiples of 64 (conv3x3: Modules.py:145-156;
+ * BasicBlock.conv3 1x1 with bias: :126).  tcgen05 implicit GEMM.  x [B,H,W,Cin] bf16, w [Cout][ks*ks][Cin] bf16, bias [Cout] f32 or NULL,
+ * y [B,H,W,Cout] f32.  If stats != NULL, stats[B][Cout][2] f32 += per-image (sum, sum of squares) of y over H*W (zero it first). */
+int gq_conv_tc(const void* x, const void* w, const float* bias, float* y, float* stats, int B, int H, int W, int Cin, int Cout, int ks, void* stream);
+/* Perception_Module.C1 = conv3x3(4, 64), no bias (Modules.py:163): x [B,4,H,W] f32 NCHW, w [64][3][3][4] f32, y [B,H,W,64] bf16 */
+int gq_conv_first(const float* x, const float* w, void* y, int B, int H, int W, void* stream);
+/* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) (Modules.py:164,166): x [B,H,W,C] -> y [B,ceil(H/2),ceil(W/2),C] */
+int gq_maxpool(const void* x, void* y, int B, int H, int W, int C, void* stream);
+/* nn.BatchNorm2d in training mode with per-image statistics + optional residual add + ReLU (BasicBlock.forward, Modules.py:128-142):
+ * y = relu((x - mean) * rsqrt(var + eps) * gamma + beta [+ identity]); x, identity [B,HW,C] f32, stats from gq_conv_tc, y bf16 */
+int gq_bn_act(const float* x, const float* stats, const float* gamma, const float* beta, const float* identity, void* y, int B, int HW, int C,
+              float eps, void* stream);
+/* nn.UpsamplingBilinear2d(scale_factor=2) (align_corners=True) (Modules.py:248,250): x [B,H,W,C] -> y [B,2H,2W,C] */
+int gq_upsample2x(const void* x, void* y, int B, int H, int W, int C, void* stream);
+/* Grasping_Module_multidiscrete.C1 = nn.Conv2d(64, A, 1) + squeeze + Sigmoid (Modules.py:251,281-283): x [B,HW,64] bf16, w [A][64] f32,
+ * bias [A] f32 -> q [B,A,HW] f32 (the reference's NCHW output layout) */
+int gq_head(const void* x, const float* w, const float* bias, float* q, int B, int HW, int A, void* stream);
+/* output.view(-1).max(0) per image (Grasping_Agent_multidiscrete.py:295-299): q [B,n] -> idx [B] int32 (rot*HW + y*W + x), val [B] f32 */
+int gq_argmax(const float* q, int B, int n, int* idx, float* val, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

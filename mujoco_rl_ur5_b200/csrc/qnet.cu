@@ -1,0 +1,340 @@
+// libgrasp_qnet.so — forward pass of the pixel-wise grasp Q-network (reference: Modules.py:308-311 MULTIDISCRETE_RESNET =
+// Perception_Module :159-193 + Grasping_Module_multidiscrete :243-287, BasicBlock :92-142) over a batch of environments.
+//
+// bf16 activations (NHWC) and weights, fp32 accumulation.  The 3x3 / 1x1 convolutions with Cin >= 64 (>99.9 % of the MACs) run
+// as implicit GEMMs on the 5th-generation tensor cores: tcgen05.mma (kind::f16, M=128, N=64/128, K=16) with the accumulator in
+// TMEM, operands gathered into shared memory in the canonical K-major no-swizzle core-matrix layout, completion tracked with
+// tcgen05.commit -> mbarrier, epilogue through tcgen05.ld.  BatchNorm uses per-image batch statistics because the reference
+// never puts the policy net in eval() and forwards one image at a time.
+//
+// C-ABI: see include/grasp_qnet.h.  No CPU fallback.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/grasp_qnet.h"
+
+typedef __nv_bfloat16 bf16;
+
+static thread_local char q_err[256] = "";
+extern "C" const char* gq_last_error(void) { return q_err; }
+#define QCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(q_err, sizeof q_err, "CUDA error: %s", cudaGetErrorString(e_)); return -2; } } while (0)
+
+// ------------------------------------------------------------------------------------------------ small PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, addr = smem_u32(bar);
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; single-thread issue
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+// shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B stored contiguously (128 B);
+// LBO = byte distance between the two 16-byte K-chunks of one MMA, SBO = byte distance between 8-row groups
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;                // base offset 0, lbo mode 0, layout type 0 = SWIZZLE_NONE
+}
+// instruction descriptor kind::f16: D = F32, A = B = BF16, both K-major, shape M x N (K = 16)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------ implicit-GEMM convolution on tcgen05
+// x  [B,H,W,Cin] bf16 (NHWC), w [Cout][ks*ks][Cin] bf16, y [B,H,W,Cout] f32 (+ bias), stats [B,Cout,2] f32 += (sum, sum of squares)
+// grid (ceil(H*W/128), Cout/BLOCK_N, B), 128 threads.  One CTA = 128 output pixels x BLOCK_N output channels of one image.
+#define BM 128
+#define BK 64
+template <int BLOCK_N>
+__global__ void __launch_bounds__(128) k_conv_tc(const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ bias,
+                                                 float* __restrict__ y, float* __restrict__ stats, int H, int W, int Cin, int Cout, int ks) {
+  constexpr int A_STAGE = BM * BK * 2, B_STAGE = BLOCK_N * BK * 2;  // bytes
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                     // 2 stages
+  uint8_t* sB = smem + 2 * A_STAGE;       // 2 stages
+  uint64_t* mbar = (uint64_t*)(smem + 2 * A_STAGE + 2 * B_STAGE);  // [0,1] stage free, [2] accumulator ready
+  uint32_t* tmem_slot = (uint32_t*)(mbar + 3);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HW = H * W, m0 = blockIdx.x * BM, n0 = blockIdx.y * BLOCK_N, b = blockIdx.z;
+  const int pad = ks / 2, taps = ks * ks, kchunks = Cin / BK, nk = taps * kchunks;
+  if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_init(&mbar[2], 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(tmem_slot, BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tacc = *tmem_slot;
+  constexpr uint32_t idesc = make_idesc(BM, BLOCK_N);
+  // this thread's A row (output pixel) and B row (output channel)
+  const int m = m0 + tid;
+  const bool mvalid = m < HW;
+  const int oh = mvalid ? m / W : 0, ow = mvalid ? m % W : 0;
+  const bf16* xb = x + (size_t)b * HW * Cin;
+  uint32_t phase[2] = {0, 0};
+  for (int kb = 0; kb < nk; kb++) {
+    const int s = kb & 1, tap = kb / kchunks, c0 = (kb % kchunks) * BK;
+    if (kb >= 2) { mbar_wait(&mbar[s], phase[s]); phase[s] ^= 1; }  // the MMAs that read this stage two iterations ago are done
+    // ---- gather A: 64 input channels of the tap-shifted pixel (zero outside the image), 8 x 16 B -> chunk-major smem
+    {
+      const int ih = oh + tap / ks - pad, iw = ow + tap % ks - pad;
+      const bool ok = mvalid && ih >= 0 && ih < H && iw >= 0 && iw < W;
+      const uint4* src = (const uint4*)(xb + ((size_t)ih * W + iw) * Cin + c0);
+      uint4* dst = (uint4*)(sA + s * A_STAGE);
+#pragma unroll
+      for (int c = 0; c < 8; c++) dst[c * BM + tid] = ok ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+    }
+    // ---- gather B: 64 K-values of BLOCK_N output channels
+    {
+      uint4* dst = (uint4*)(sB + s * B_STAGE);
+      for (int r = tid; r < BLOCK_N; r += 128) {
+        const uint4* src = (const uint4*)(w + ((size_t)(n0 + r) * taps + tap) * Cin + c0);
+#pragma unroll
+        for (int c = 0; c < 8; c++) dst[c * BLOCK_N + r] = __ldg(src + c);
+      }
+    }
+    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(sA + s * A_STAGE), b_base = smem_u32(sB + s * B_STAGE);
+#pragma unroll
+      for (int k = 0; k < BK / 16; k++) {  // UMMA_K = 16 bf16 = two 16-byte chunks
+        uint64_t adesc = make_smem_desc(a_base + k * 2 * (BM * 16), BM * 16, 128);
+        uint64_t bdesc = make_smem_desc(b_base + k * 2 * (BLOCK_N * 16), BLOCK_N * 16, 128);
+        umma_bf16(tacc, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+      }
+      umma_commit(&mbar[s]);                 // frees the stage when these MMAs have read it
+      if (kb == nk - 1) umma_commit(&mbar[2]);  // accumulator complete
+    }
+  }
+  mbar_wait(&mbar[2], 0);
+  tc_fence_after();
+  // ---- epilogue: TMEM -> registers -> global fp32 (+bias), per-channel batch-norm statistics
+  float* yrow = y + ((size_t)b * HW + m) * Cout + n0;
+  for (int cb = 0; cb < BLOCK_N; cb += 32) {
+    float v[32];
+    tmem_ld32(tacc + ((uint32_t)(warp * 32) << 16) + cb, v);
+    if (bias) {
+#pragma unroll
+      for (int i = 0; i < 32; i++) v[i] += bias[n0 + cb + i];
+    }
+    if (mvalid) {
+      float4* dst = (float4*)(yrow + cb);
+#pragma unroll
+      for (int i = 0; i < 8; i++) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+    if (stats) {
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        float s1 = mvalid ? v[i] : 0.f, s2 = s1 * s1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+        if (lane == 0) { atomicAdd(stats + ((size_t)b * Cout + n0 + cb + i) * 2, s1); atomicAdd(stats + ((size_t)b * Cout + n0 + cb + i) * 2 + 1, s2); }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tacc, BLOCK_N);
+}
+
+// ------------------------------------------------------------------------------------------------ small layers
+// first conv: x [B,4,H,W] f32 (NCHW, the agent's tensor), w [64][3][3][4] f32 -> y [B,H,W,64] bf16; no BN / ReLU follows (Modules.py:176)
+__global__ void k_conv_first(const float* __restrict__ x, const float* __restrict__ w, bf16* __restrict__ y, int B, int H, int W) {
+  __shared__ float sw[64 * 36];
+  for (int i = threadIdx.x; i < 64 * 36; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  int p = blockIdx.x * blockDim.x + threadIdx.x, HW = H * W;
+  if (p >= B * HW) return;
+  int b = p / HW, oh = (p % HW) / W, ow = p % W;
+  float in[36];
+#pragma unroll
+  for (int t = 0; t < 9; t++) {
+    int ih = oh + t / 3 - 1, iw = ow + t % 3 - 1;
+    bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+#pragma unroll
+    for (int c = 0; c < 4; c++) in[t * 4 + c] = ok ? x[((size_t)(b * 4 + c) * H + ih) * W + iw] : 0.f;
+  }
+  bf16* out = y + (size_t)p * 64;
+  for (int co = 0; co < 64; co += 2) {
+    float a0 = 0, a1 = 0;
+#pragma unroll
+    for (int k = 0; k < 36; k++) { a0 += in[k] * sw[co * 36 + k]; a1 += in[k] * sw[(co + 1) * 36 + k]; }
+    *(__nv_bfloat162*)(out + co) = __floats2bfloat162_rn(a0, a1);
+  }
+}
+// MaxPool2d(kernel 3, stride 2, padding 1) on NHWC bf16
+__global__ void k_maxpool(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int H, int W, int C) {
+  int OH = (H + 1) / 2, OW = (W + 1) / 2;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)B * OH * OW * (C / 2);
+  if (i >= n) return;
+  int c2 = i % (C / 2);
+  size_t p = i / (C / 2);
+  int ow = p % OW, oh = (p / OW) % OH, b = p / ((size_t)OW * OH);
+  float m0 = -3.0e38f, m1 = -3.0e38f;
+  for (int dh = -1; dh <= 1; dh++) for (int dw = -1; dw <= 1; dw++) {
+    int ih = 2 * oh + dh, iw = 2 * ow + dw;
+    if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+    float2 v = __bfloat1622float2(*(const __nv_bfloat162*)(x + (((size_t)b * H + ih) * W + iw) * C + 2 * c2));
+    m0 = fmaxf(m0, v.x); m1 = fmaxf(m1, v.y);
+  }
+  *(__nv_bfloat162*)(y + p * C + 2 * c2) = __floats2bfloat162_rn(m0, m1);
+}
+// y = relu( (x - mean) * rstd * gamma + beta [+ identity] ), per-image statistics from `stats` (sum, sumsq over H*W); fp32 in, bf16 out
+__global__ void k_bn_act(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                         const float* __restrict__ identity, bf16* __restrict__ y, int B, int HW, int C, float eps) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)B * HW * C;
+  if (i >= n) return;
+  int c = i % C, b = i / ((size_t)HW * C);
+  float s1 = stats[((size_t)b * C + c) * 2], s2 = stats[((size_t)b * C + c) * 2 + 1];
+  float mean = s1 / HW, var = fmaxf(s2 / HW - mean * mean, 0.f);  // biased variance, as BatchNorm uses for normalisation
+  float v = (x[i] - mean) * rsqrtf(var + eps) * gamma[c] + beta[c];
+  if (identity) v += identity[i];
+  y[i] = __float2bfloat16(fmaxf(v, 0.f));
+}
+// nn.UpsamplingBilinear2d(scale_factor=2) = bilinear, align_corners=True; NHWC bf16
+__global__ void k_upsample2x(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int H, int W, int C) {
+  int OH = 2 * H, OW = 2 * W;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)B * OH * OW * (C / 2);
+  if (i >= n) return;
+  int c2 = i % (C / 2);
+  size_t p = i / (C / 2);
+  int ow = p % OW, oh = (p / OW) % OH, b = p / ((size_t)OW * OH);
+  float fy = oh * (float)(H - 1) / (float)(OH - 1), fx = ow * (float)(W - 1) / (float)(OW - 1);
+  int y0 = (int)fy, x0 = (int)fx, y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  float wy = fy - y0, wx = fx - x0;
+  auto at = [&](int yy, int xx) { return __bfloat1622float2(*(const __nv_bfloat162*)(x + (((size_t)b * H + yy) * W + xx) * C + 2 * c2)); };
+  float2 a = at(y0, x0), bb = at(y0, x1), cc = at(y1, x0), d = at(y1, x1);
+  float r0 = (a.x * (1 - wx) + bb.x * wx) * (1 - wy) + (cc.x * (1 - wx) + d.x * wx) * wy;
+  float r1 = (a.y * (1 - wx) + bb.y * wx) * (1 - wy) + (cc.y * (1 - wx) + d.y * wx) * wy;
+  *(__nv_bfloat162*)(y + p * C + 2 * c2) = __floats2bfloat162_rn(r0, r1);
+}
+// last layer: conv1x1 64 -> A (+bias) and sigmoid; x [B,HW,64] bf16, w [A][64] f32 -> q [B,A,HW] f32 (NCHW like the reference output)
+__global__ void k_head(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ q, int B, int HW, int A) {
+  __shared__ float sw[8 * 64 + 8];
+  for (int i = threadIdx.x; i < A * 64; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < A) sw[8 * 64 + threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (size_t)B * HW) return;
+  int b = p / HW, pix = p % HW;
+  float in[64];
+  const __nv_bfloat162* src = (const __nv_bfloat162*)(x + p * 64);
+#pragma unroll
+  for (int c = 0; c < 32; c++) { float2 v = __bfloat1622float2(src[c]); in[2 * c] = v.x; in[2 * c + 1] = v.y; }
+  for (int a = 0; a < A; a++) {
+    float acc = sw[8 * 64 + a];
+#pragma unroll
+    for (int c = 0; c < 64; c++) acc += in[c] * sw[a * 64 + c];
+    q[((size_t)b * A + a) * HW + pix] = 1.f / (1.f + __expf(-acc));
+  }
+}
+// flat arg-max over the A*HW Q-values of every image (Grasping_Agent_multidiscrete.py:295-299): idx = rot*HW + y*W + x
+__global__ void k_argmax(const float* __restrict__ q, int n, int* __restrict__ idx, float* __restrict__ val) {
+  __shared__ float sv[256];
+  __shared__ int si[256];
+  const float* qb = q + (size_t)blockIdx.x * n;
+  float bv = -1.f; int bi = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { float v = qb[i]; if (v > bv) { bv = v; bi = i; } }
+  sv[threadIdx.x] = bv; si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { float ov = sv[threadIdx.x + o]; int oi = si[threadIdx.x + o]; if (ov > sv[threadIdx.x] || (ov == sv[threadIdx.x] && oi < si[threadIdx.x])) { sv[threadIdx.x] = ov; si[threadIdx.x] = oi; } }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { idx[blockIdx.x] = si[0]; val[blockIdx.x] = sv[0]; }
+}
+
+// ------------------------------------------------------------------------------------------------ C-ABI
+extern "C" const char* gq_version(void) { return "grasp_qnet 0.1 sm_100a bf16 tcgen05"; }
+
+extern "C" int gq_conv_tc(const void* x, const void* w, const float* bias, float* y, float* stats, int B, int H, int W, int Cin, int Cout, int ks, void* stream) {
+  if (!x || !w || !y || (ks != 1 && ks != 3) || Cin % 64 || Cout % 64) { snprintf(q_err, sizeof q_err, "gq_conv_tc: bad argument"); return -1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  int bn = (Cout % 128 == 0) ? 128 : 64;
+  dim3 grid((H * W + BM - 1) / BM, Cout / bn, B);
+  size_t smem = 2 * (BM * BK * 2) + 2 * ((size_t)bn * BK * 2) + 64;
+  if (bn == 128) {
+    QCK(cudaFuncSetAttribute(k_conv_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_conv_tc<128><<<grid, 128, smem, st>>>((const bf16*)x, (const bf16*)w, bias, y, stats, H, W, Cin, Cout, ks);
+  } else {
+    QCK(cudaFuncSetAttribute(k_conv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_conv_tc<64><<<grid, 128, smem, st>>>((const bf16*)x, (const bf16*)w, bias, y, stats, H, W, Cin, Cout, ks);
+  }
+  QCK(cudaGetLastError());
+  return 0;
+}
+extern "C" int gq_conv_first(const float* x, const float* w, void* y, int B, int H, int W, void* stream) {
+  k_conv_first<<<(B * H * W + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, w, (bf16*)y, B, H, W);
+  QCK(cudaGetLastError());
+  return 0;
+}
+extern "C" int gq_maxpool(const void* x, void* y, int B, int H, int W, int C, void* stream) {
+  size_t n = (size_t)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 2);
+  k_maxpool<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, B, H, W, C);
+  QCK(cudaGetLastError());
+  return 0;
+}
+extern "C" int gq_bn_act(const float* x, const float* stats, const float* gamma, const float* beta, const float* identity, void* y, int B, int HW, int C,
+                         float eps, void* stream) {
+  size_t n = (size_t)B * HW * C;
+  k_bn_act<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, stats, gamma, beta, identity, (bf16*)y, B, HW, C, eps);
+  QCK(cudaGetLastError());
+  return 0;
+}
+extern "C" int gq_upsample2x(const void* x, void* y, int B, int H, int W, int C, void* stream) {
+  size_t n = (size_t)B * 4 * H * W * (C / 2);
+  k_upsample2x<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, B, H, W, C);
+  QCK(cudaGetLastError());
+  return 0;
+}
+extern "C" int gq_head(const void* x, const float* w, const float* bias, float* q, int B, int HW, int A, void* stream) {
+  if (A > 8) { snprintf(q_err, sizeof q_err, "gq_head: at most 8 action channels"); return -1; }
+  k_head<<<(unsigned)(((size_t)B * HW + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const bf16*)x, w, bias, q, B, HW, A);
+  QCK(cudaGetLastError());
+  return 0;
+}
+extern "C" int gq_argmax(const float* q, int B, int n, int* idx, float* val, void* stream) {
+  k_argmax<<<B, 256, 0, (cudaStream_t)stream>>>(q, n, idx, val);
+  QCK(cudaGetLastError());
+  return 0;
+}
