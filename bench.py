@@ -283,6 +283,38 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dist.all_reduce(ten, op=dist.ReduceOp.SUM)
     e2e_value = float(ten[0]) / float(te[0])
+    # ---- a16: Q-network forward (bf16 tcgen05) on the observations of the envs, chunked; extra object, not the headline
+    qinfo = None
+    if args.qnet_images > 0:
+        from mujoco_rl_ur5_b200.qnet import QNetForward, make_torch_qnet
+
+        torch.manual_seed(0)
+        qf = QNetForward(make_torch_qnet(6).state_dict(), local, max_batch=args.qnet_chunk)
+        nimg = min(args.qnet_images, N)
+        obs = env.current_observation
+        sub = {"rgb": obs["rgb"][:nimg], "depth": obs["depth"][:nimg]}
+        for _ in range(2):
+            act, _ = qf.greedy(qf.forward(qf.obs_to_state(sub, 1.1)))
+        barrier()
+        l_q0 = qf.launches
+        q0, q1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        q0.record()
+        for _ in range(args.qnet_reps):
+            act, _ = qf.greedy(qf.forward(qf.obs_to_state(sub, 1.1)))
+        q1.record()
+        barrier()
+        qms = q0.elapsed_time(q1) / args.qnet_reps
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        tf = nimg * 41.99424e9 / (qms * 1e-3) / 1e12
+        pk = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        qinfo = {"images": nimg, "chunk": args.qnet_chunk, "ms_per_batch": qms, "images_per_s": nimg / (qms * 1e-3), "tflops": tf,
+                 "roofline": {"bound": "tensor", "achieved": tf, "peak": pk, "unit": "TFLOP/s", "frac": tf / pk,
+                              "note": "41.99 GFLOP per 200x200 image (SURVEY 8d); peak = " + ("measured sustained cuBLAS bf16" if peaks else "fallback")},
+                 "kernels_per_batch": (qf.launches - l_q0) // max(args.qnet_reps, 1)}
     status = eng.status()
     status_or = int(torch.bitwise_or(status[0], status.max()).item()) if N else 0
     n_flag = int((status != 0).sum().item())
@@ -313,7 +345,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step, "d2h_bytes_per_step": env.d2h_bytes_per_step,
                     "steps": args.e2e_steps, "note": "BatchedGraspEnv.step: pinned host actions -> pixel_2_world -> full grasp attempts -> RGB-D render -> host rewards"},
             "gpu_launches": int(l1 - l0), "substep_kernel_launches": int(s1 - s0),
-            "clocks": clocks, "env_status_flags": {"envs_flagged": n_flag, "or": status_or},
+            "clocks": clocks, "env_status_flags": {"envs_flagged": n_flag, "or": status_or}, "qnet": qinfo,
         }
         print(json.dumps(out))
     if world > 1:
@@ -330,6 +362,9 @@ def main():
     ap.add_argument("--chunk", type=int, default=256, help="control-loop iterations per busy env and step")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--qnet-images", type=int, default=256, help="images for the Q-net forward leg (0 = skip)")
+    ap.add_argument("--qnet-chunk", type=int, default=64)
+    ap.add_argument("--qnet-reps", type=int, default=3)
     ap.add_argument("--ref-step-seconds", type=float, default=3.0, help="--impl reference: wall-time budget per worker and step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

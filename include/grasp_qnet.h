@@ -33,6 +33,11 @@ int gq_upsample2x(const void* x, void* y, int B, int H, int W, int C, void* stre
 /* Grasping_Module_multidiscrete.C1 = nn.Conv2d(64, A, 1) + squeeze + Sigmoid (Modules.py:251,281-283): x [B,HW,64] bf16, w [A][64] f32,
  * bias [A] f32 -> q [B,A,HW] f32 (the reference's NCHW output layout) */
 int gq_head(const void* x, const float* w, const float* bias, float* q, int B, int HW, int A, void* stream);
+/* Grasp_Agent.transform_observation(normalize=True, jitter_and_noise=False) batched (Grasping_Agent_multidiscrete.py:301-368):
+ * rgb [B,HW,3] u8, depth [B,HW] f32 metres -> state [B,4,HW] f32 (rgb/255, depth clipped at depth_threshold, negated, min-max per image);
+ * scratch_minmax [B,2] f32 */
+int gq_obs_to_state(const unsigned char* rgb, const float* depth, float depth_threshold, float* scratch_minmax, float* state, int B, int HW,
+                    void* stream);
 /* output.view(-1).max(0) per image (Grasping_Agent_multidiscrete.py:295-299): q [B,n] -> idx [B] int32 (rot*HW + y*W + x), val [B] f32 */
 int gq_argmax(const float* q, int B, int n, int* idx, float* val, void* stream);
 

@@ -284,7 +284,41 @@ __global__ void k_argmax(const float* __restrict__ q, int n, int* __restrict__ i
   if (threadIdx.x == 0) { idx[blockIdx.x] = si[0]; val[blockIdx.x] = sv[0]; }
 }
 
+// Grasp_Agent.transform_observation with normalize=True, jitter_and_noise=False (Grasping_Agent_multidiscrete.py:301-368), batched:
+// depth clipped at `thr`, negated, min-max normalised per image; rgb u8 -> [0,1]; output state [B,4,H,W] f32 (r,g,b,depth)
+__global__ void k_obs_minmax(const float* __restrict__ depth, int HW, float thr, float* __restrict__ mm) {
+  __shared__ float smin[256], smax[256];
+  const float* d = depth + (size_t)blockIdx.x * HW;
+  float lo = 3.0e38f, hi = -3.0e38f;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) { float v = -fminf(d[i], thr); lo = fminf(lo, v); hi = fmaxf(hi, v); }
+  smin[threadIdx.x] = lo; smax[threadIdx.x] = hi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { smin[threadIdx.x] = fminf(smin[threadIdx.x], smin[threadIdx.x + o]); smax[threadIdx.x] = fmaxf(smax[threadIdx.x], smax[threadIdx.x + o]); }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { mm[2 * blockIdx.x] = smin[0]; mm[2 * blockIdx.x + 1] = smax[0]; }
+}
+__global__ void k_obs_state(const unsigned char* __restrict__ rgb, const float* __restrict__ depth, const float* __restrict__ mm, float thr, int B, int HW,
+                            float* __restrict__ state) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * HW) return;
+  int b = i / HW, p = i % HW;
+  float lo = mm[2 * b], hi = mm[2 * b + 1];
+  float* out = state + (size_t)b * 4 * HW + p;
+  out[0] = rgb[3 * i] * (1.f / 255.f); out[HW] = rgb[3 * i + 1] * (1.f / 255.f); out[2 * HW] = rgb[3 * i + 2] * (1.f / 255.f);
+  out[3 * (size_t)HW] = (-fminf(depth[i], thr) - lo) / (hi - lo);
+}
+
 // ------------------------------------------------------------------------------------------------ C-ABI
+extern "C" int gq_obs_to_state(const unsigned char* rgb, const float* depth, float depth_threshold, float* scratch_minmax, float* state, int B, int HW,
+                               void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  k_obs_minmax<<<B, 256, 0, st>>>(depth, HW, depth_threshold, scratch_minmax);
+  k_obs_state<<<(unsigned)(((size_t)B * HW + 255) / 256), 256, 0, st>>>(rgb, depth, scratch_minmax, depth_threshold, B, HW, state);
+  QCK(cudaGetLastError());
+  return 0;
+}
 extern "C" const char* gq_version(void) { return "grasp_qnet 0.1 sm_100a bf16 tcgen05"; }
 
 extern "C" int gq_conv_tc(const void* x, const void* w, const float* bias, float* y, float* stats, int B, int H, int W, int Cin, int Cout, int ks, void* stream) {

@@ -20,7 +20,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 QLIB_PATH = os.path.join(_HERE, "csrc", "libgrasp_qnet.so")
 _QLIB = None
-QSYMBOLS = ["gq_last_error", "gq_version", "gq_conv_tc", "gq_conv_first", "gq_maxpool", "gq_bn_act", "gq_upsample2x", "gq_head", "gq_argmax"]
+QSYMBOLS = ["gq_last_error", "gq_version", "gq_conv_tc", "gq_conv_first", "gq_maxpool", "gq_bn_act", "gq_upsample2x", "gq_head", "gq_argmax", "gq_obs_to_state"]
 
 
 def load_qnet_library():
@@ -39,6 +39,7 @@ def load_qnet_library():
         L.gq_upsample2x.argtypes = [P, P, I, I, I, I, P]
         L.gq_head.argtypes = [P, P, P, P, I, I, I, P]
         L.gq_argmax.argtypes = [P, I, I, P, P, P]
+        L.gq_obs_to_state.argtypes = [P, P, F, P, P, I, I, P]
         _QLIB = L
     return _QLIB
 
@@ -203,6 +204,18 @@ class QNetForward:
         state = state.to(self.dev, t.float32).contiguous()
         outs = [self._forward_chunk(state[i:i + self.max_batch]) for i in range(0, state.shape[0], self.max_batch)]
         return outs[0] if len(outs) == 1 else t.cat(outs, dim=0)
+
+    def obs_to_state(self, obs, depth_threshold=1.1):
+        """batched deterministic transform_observation: obs dict of device tensors (rgb u8 [B,H,W,3], depth f32 [B,H,W]) -> [B,4,H,W] f32.
+        depth_threshold = cam height - TABLE_HEIGHT + 0.01 = 1.1 (Grasping_Agent_multidiscrete.py:130-135)"""
+        t = self.torch
+        rgb, depth = obs["rgb"].contiguous(), obs["depth"].contiguous()
+        B, H, W = depth.shape
+        state = t.empty((B, 4, H, W), dtype=t.float32, device=self.dev)
+        mm = t.empty((B, 2), dtype=t.float32, device=self.dev)
+        self._ck(self.L.gq_obs_to_state(self._p(rgb), self._p(depth), float(depth_threshold), self._p(mm), self._p(state), B, H * W, self._stream()), "gq_obs_to_state")
+        self.launches += 1
+        return state
 
     def greedy(self, q):
         """flat arg-max per image and its split into (pixel index, rotation index) as transform_action does
