@@ -49,7 +49,7 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
   __syncwarp();
   LANE_LOOP(ci, ncon) {
     if (!wi[L.i_cact + ci]) continue;
-    int t1 = tree_of_body(wi[L.i_cb1 + ci]), t2 = tree_of_body(wi[L.i_cb2 + ci]);
+    int t1 = wi[L.i_ct1 + ci], t2 = wi[L.i_ct2 + ci];
     if (t1 >= 0 && t2 >= 0 && t1 != t2) { tcoupled[t1] = 1; tcoupled[t2] = 1; }
   }
   LANE_LOOP(i, nsr) {
@@ -80,17 +80,14 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
       for (int ci = 0; ci < ncon; ci++) {
         int mask = wi[L.i_cact + ci];
         if (!mask) continue;
-        int b1 = wi[L.i_cb1 + ci], b2 = wi[L.i_cb2 + ci];
-        if (tree_of_body(b1) != t && tree_of_body(b2) != t) continue;
+        int t1 = wi[L.i_ct1 + ci], t2 = wi[L.i_ct2 + ci];
+        if (t1 != t && t2 != t) continue;
         const double* c = ws + L.con + ci * L.cstride;
         int dim = wi[L.i_cdim + ci];
-        // sign of my dof in the contact's dof list (chains of both bodies minus their common ancestors)
-        double sgn = 0;
-        int i1 = m.body_lastdof[b1], i2 = m.body_lastdof[b2];
-        while (i1 != i2) {
-          if (i2 > i1) { if (i2 == mydof) sgn = 1.0; i2 = m.dof_parentid[i2]; }
-          else { if (i1 == mydof) sgn = -1.0; i1 = m.dof_parentid[i1]; }
-        }
+        // sign of my dof in the contact's dof list (chains of both bodies minus their common ancestors), from the per-body
+        // bit masks over the tree-local dof index
+        unsigned m1 = t1 == t ? (unsigned)m.body_chainmask[wi[L.i_cb1 + ci]] : 0u, m2 = t2 == t ? (unsigned)m.body_chainmask[wi[L.i_cb2 + ci]] : 0u;
+        double sgn = ((m2 & ~m1) >> l & 1u) ? 1.0 : (((m1 & ~m2) >> l & 1u) ? -1.0 : 0.0);
         double J[6] = {0, 0, 0, 0, 0, 0}, tw[6] = {0, 0, 0, 0, 0, 0};
         if (sgn != 0) { jac_column(c, dim, cdof + 6 * mydof, sgn, J); weight_column(c, dim, mask, J, tw); }
         for (int f = 0; f < nt; f++) {
@@ -121,7 +118,7 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
   // ---- coupled trees, pass 1: row envelopes (a coupled row reaches down to the lowest dof it shares a contact with) ...
   for (int ci = 0; ci < ncon; ci++) {
     if (!wi[L.i_cact + ci]) continue;
-    int b1 = wi[L.i_cb1 + ci], b2 = wi[L.i_cb2 + ci], t1 = tree_of_body(b1), t2 = tree_of_body(b2);
+    int b1 = wi[L.i_cb1 + ci], b2 = wi[L.i_cb2 + ci], t1 = wi[L.i_ct1 + ci], t2 = wi[L.i_ct2 + ci];
     if (!((t1 >= 0 && tcoupled[t1]) || (t2 >= 0 && tcoupled[t2]))) continue;
     int i1 = m.body_lastdof[b1], i2 = m.body_lastdof[b2], n = 0, mydof = -1, minE = 0x7fffffff;
     while (i1 != i2) {
@@ -153,7 +150,7 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
   for (int ci = 0; ci < ncon; ci++) {
     int mask = wi[L.i_cact + ci];
     if (!mask) continue;
-    int b1 = wi[L.i_cb1 + ci], b2 = wi[L.i_cb2 + ci], t1 = tree_of_body(b1), t2 = tree_of_body(b2);
+    int b1 = wi[L.i_cb1 + ci], b2 = wi[L.i_cb2 + ci], t1 = wi[L.i_ct1 + ci], t2 = wi[L.i_ct2 + ci];
     if (!((t1 >= 0 && tcoupled[t1]) || (t2 >= 0 && tcoupled[t2]))) continue;
     const double* c = ws + L.con + ci * L.cstride;
     int dim = wi[L.i_cdim + ci];
@@ -195,8 +192,68 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
   __syncwarp();
 }
 
-// x := -H^-1 g.  Uncoupled trees: dense left-looking Cholesky + substitutions, one lane per tree.  Coupled trees: skyline
-// right-looking Cholesky with the whole warp (each lane owns rows lane, lane+32, ...).
+// Dense Cholesky + forward/backward substitution of one tree block (rows lo .. lo+nt-1 of the packed matrix, nt <= GE_GROUP)
+// inside an 8-lane group: lane l owns row lo + l.  x[row] := sign * (H_block^-1 g)[row].
+__device__ __forceinline__ void group_chol_solve(double* H, int lo, int nt, int l, unsigned gmask, const double* g_, double* x, double sign) {
+  const int row = lo + l;
+  const bool mine = l < nt;
+  for (int j = 0; j < nt; j++) {
+    double d = H[HIDX(lo + j, lo + j)];
+    if (d < GE_MINVAL) d = GE_MINVAL;
+    double ljj = sqrt(d), inv = 1.0 / ljj;
+    __syncwarp(gmask);
+    if (mine && l > j) H[HIDX(row, lo + j)] *= inv;
+    if (l == j) H[HIDX(row, row)] = ljj;
+    __syncwarp(gmask);
+    if (mine && l > j) {
+      double lij = H[HIDX(row, lo + j)];
+      for (int k = j + 1; k <= l; k++) H[HIDX(row, lo + k)] -= lij * H[HIDX(lo + k, lo + j)];
+    }
+    __syncwarp(gmask);
+  }
+  double y = mine ? g_[row] : 0.0;  // L y = g (column oriented): after column j every later row subtracts L[row][j] y_j
+  for (int j = 0; j < nt; j++) {
+    double yj = __shfl_sync(gmask, y, j, GE_GROUP) / H[HIDX(lo + j, lo + j)];
+    if (l == j) y = yj;
+    else if (mine && l > j) y -= H[HIDX(row, lo + j)] * yj;
+  }
+  for (int i = nt - 1; i >= 0; i--) {  // L^T x = y
+    double xi = __shfl_sync(gmask, y, i, GE_GROUP) / H[HIDX(lo + i, lo + i)];
+    if (l == i) y = xi;
+    else if (mine && l < i) y -= H[HIDX(lo + i, row)] * xi;
+  }
+  if (mine) x[row] = sign * y;
+}
+
+// x := (M + hdamp * diag(damping))^-1 x  for the block-diagonal (per kinematic tree) mass matrix, through dense per-tree
+// Cholesky factors in the (currently free) Hessian storage.  Replaces the tree-sparse L^T D L factor/solve when every tree fits
+// a lane group; returns false (nothing done) otherwise so that the caller can fall back.
+__device__ __noinline__ bool mass_block_solve(double* ws, double* x, double hdamp, int lane) {
+  const DevModel& m = c_m; const Layout& L = c_L;
+  for (int t = 0; t < m.ntree; t++) if (m.tree_dofnum[t] > GE_GROUP) return false;
+  double* H = ws + L.H;
+  const double* qM = ws + L.qM;
+  LANE_LOOP(i, m.nv) {
+    int root = m.tree_dofadr[m.dof_treeindex[i]];
+    for (int j = root; j <= i; j++) H[HIDX(i, j)] = 0;
+    int a = m.dof_Madr[i], k = 0;
+    for (int j = i; j >= 0; j = m.dof_parentid[j], k++) H[HIDX(i, j)] = qM[a + k];
+    if (hdamp != 0.0) H[HIDX(i, i)] += hdamp * m.dof_damping[i];
+  }
+  __syncwarp();
+  const int g = lane / GE_GROUP, l = lane % GE_GROUP;
+  const unsigned gmask = ((1u << GE_GROUP) - 1u) << (g * GE_GROUP);
+  for (int t0 = 0; t0 < m.ntree; t0 += 32 / GE_GROUP) {
+    int t = t0 + g;
+    if (t >= m.ntree) continue;
+    group_chol_solve(H, m.tree_dofadr[t], m.tree_dofnum[t], l, gmask, x, x, 1.0);
+  }
+  __syncwarp();
+  return true;
+}
+
+// x := -H^-1 g.  Uncoupled trees: 8-lane groups (group_chol_solve).  Coupled trees: skyline right-looking Cholesky with the
+// whole warp (each lane owns rows lane, lane+32, ...).
 __device__ __noinline__ void cholesky_solve(double* ws, const int* wi, double* x, const double* g_, int lane) {
   const DevModel& m = c_m; const Layout& L = c_L;
   double* H = ws + L.H;
@@ -205,40 +262,12 @@ __device__ __noinline__ void cholesky_solve(double* ws, const int* wi, double* x
   bool any_coupled = false;
   for (int t = 0; t < m.ntree; t++) any_coupled |= tcoupled[t] != 0;
   {
-    // uncoupled trees: right-looking Cholesky + substitutions inside an 8-lane group, lane l owns row lo + l
     const int g = lane / GE_GROUP, l = lane % GE_GROUP;
     const unsigned gmask = ((1u << GE_GROUP) - 1u) << (g * GE_GROUP);
     for (int t0 = 0; t0 < m.ntree; t0 += 32 / GE_GROUP) {
       int t = t0 + g;
       if (t >= m.ntree || tcoupled[t]) continue;  // group-uniform
-      int lo = m.tree_dofadr[t], nt = m.tree_dofnum[t], row = lo + l;
-      bool mine = l < nt;
-      for (int j = 0; j < nt; j++) {
-        double d = H[HIDX(lo + j, lo + j)];
-        if (d < GE_MINVAL) d = GE_MINVAL;
-        double ljj = sqrt(d), inv = 1.0 / ljj;
-        __syncwarp(gmask);
-        if (mine && l > j) H[HIDX(row, lo + j)] *= inv;
-        if (l == j) H[HIDX(row, row)] = ljj;
-        __syncwarp(gmask);
-        if (mine && l > j) {
-          double lij = H[HIDX(row, lo + j)];
-          for (int k = j + 1; k <= l; k++) H[HIDX(row, lo + k)] -= lij * H[HIDX(lo + k, lo + j)];
-        }
-        __syncwarp(gmask);
-      }
-      double y = mine ? g_[row] : 0.0;  // L y = g (column oriented): after column j every later row subtracts L[row][j] y_j
-      for (int j = 0; j < nt; j++) {
-        double yj = __shfl_sync(gmask, y, j, GE_GROUP) / H[HIDX(lo + j, lo + j)];
-        if (l == j) y = yj;
-        else if (mine && l > j) y -= H[HIDX(row, lo + j)] * yj;
-      }
-      for (int i = nt - 1; i >= 0; i--) {  // L^T x = y
-        double xi = __shfl_sync(gmask, y, i, GE_GROUP) / H[HIDX(lo + i, lo + i)];
-        if (l == i) y = xi;
-        else if (mine && l < i) y -= H[HIDX(lo + i, row)] * xi;
-      }
-      if (mine) x[row] = -y;
+      group_chol_solve(H, m.tree_dofadr[t], m.tree_dofnum[t], l, gmask, g_, x, -1.0);
     }
   }
   __syncwarp();

@@ -18,7 +18,7 @@ struct DevModel {
   double timestep, gravity[3], tolerance, impratio, mpr_tol, meaninertia, extent, zfar;
   int iterations, mpr_iter, any_damping, ik_base_body, ee_body;
   const double *qpos0, *body_pos, *body_quat, *body_mass, *body_ipos, *body_inertia, *body_invweight0;
-  const int *body_parentid, *body_jntadr, *body_jntnum, *body_lastdof, *body_subtreenum;
+  const int *body_parentid, *body_jntadr, *body_jntnum, *body_lastdof, *body_subtreenum, *body_chainmask;
   const int *jnt_type, *jnt_bodyid, *jnt_qposadr, *jnt_dofadr, *jnt_limited;
   const double *jnt_pos, *jnt_axis, *jnt_range, *jnt_margin, *jnt_solref, *jnt_solimp;
   const int *dof_bodyid, *dof_jntid, *dof_parentid, *dof_Madr, *dof_subtreenum, *dof_depth, *dof_treeindex, *tree_dofadr, *tree_dofnum;
@@ -52,7 +52,7 @@ struct Layout {
   // --- aliases inside scratch: solver phase
   int H, Vb, Wb;
   // --- ints
-  int i_cb1, i_cb2, i_cdim, i_cpair, i_cact, i_srA, i_srB, i_srtype, i_sract, i_cand, i_first, i_tcoupled, i_misc;
+  int i_cb1, i_cb2, i_ct1, i_ct2, i_cdim, i_cpair, i_cact, i_srA, i_srB, i_srtype, i_sract, i_cand, i_first, i_tcoupled, i_misc;
   int total_ints;
   int total_bytes;
 };

@@ -701,6 +701,7 @@ __device__ __noinline__ int stage_collision(double* ws, int* wi, int lane, int* 
     make_frame(c + C_FRAME);
     int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1], b1 = m.geom_bodyid[g1], b2 = m.geom_bodyid[g2], dim = m.pair_condim[p];
     cb1[i] = b1; cb2[i] = b2; cdim[i] = dim;
+    { int d1 = m.body_lastdof[b1], d2 = m.body_lastdof[b2]; wi[L.i_ct1 + i] = d1 < 0 ? -1 : m.dof_treeindex[d1]; wi[L.i_ct2 + i] = d2 < 0 ? -1 : m.dof_treeindex[d2]; }
     const double* f = m.pair_friction + 3 * p;
     double mu[5] = {f[0], f[0], f[1], f[2], f[2]};
     for (int k = 0; k < dim - 1; k++) c[C_MU + k] = mu[k];

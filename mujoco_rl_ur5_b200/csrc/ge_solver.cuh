@@ -178,22 +178,26 @@ __device__ __noinline__ double nt_update(double* ws, int* wi, int ncon, int nsr,
   }
   cost = warp_sum(cost);
   __syncwarp();
-  // J^T f
-  double *Wb = ws + L.Wb, *Wsub = ws + L.Vb;
+  // J^T f: one lane per contact forms the contact wrench about the world origin once (scratch: the Hessian storage, free
+  // between two Newton directions), one lane per body then adds the wrenches of its contacts in contact order
+  double *Wb = ws + L.Wb, *Wsub = ws + L.Vb, *Wc = ws + L.H;
+  LANE_LOOP(i, ncon) {
+    const double* c = ws + L.con + i * L.cstride;
+    int dim = wi[L.i_cdim + i];
+    double f[3] = {0, 0, 0}, tq[3], tr[3] = {0, 0, 0};
+    for (int k = 0; k < dim && k < 3; k++) v3addscl(f, f, c + C_FRAME + 3 * k, c[jv + k]);
+    for (int k = 3; k < dim; k++) v3addscl(tr, tr, c + C_FRAME + 3 * (k - 3), c[jv + k]);
+    v3cross(tq, c + C_POS, f); v3add(tq, tq, tr);
+    for (int k = 0; k < 3; k++) { Wc[6 * i + k] = tq[k]; Wc[6 * i + 3 + k] = f[k]; }
+  }
+  __syncwarp();
   LANE_LOOP(b, m.nbody) {
     double w[6] = {0, 0, 0, 0, 0, 0};
     if (m.body_lastdof[b] >= 0)
       for (int i = 0; i < ncon; i++) {
         int b1 = wi[L.i_cb1 + i], b2 = wi[L.i_cb2 + i];
-        if (b1 != b && b2 != b) continue;
-        const double* c = ws + L.con + i * L.cstride;
-        int dim = wi[L.i_cdim + i];
-        double f[3] = {0, 0, 0}, tq[3], tr[3] = {0, 0, 0};
-        for (int k = 0; k < dim && k < 3; k++) v3addscl(f, f, c + C_FRAME + 3 * k, c[jv + k]);
-        for (int k = 3; k < dim; k++) v3addscl(tr, tr, c + C_FRAME + 3 * (k - 3), c[jv + k]);
-        v3cross(tq, c + C_POS, f); v3add(tq, tq, tr);
-        double s = (b2 == b ? 1.0 : 0.0) - (b1 == b ? 1.0 : 0.0);
-        for (int k = 0; k < 3; k++) { w[k] += s * tq[k]; w[3 + k] += s * f[k]; }
+        if (b2 == b) for (int k = 0; k < 6; k++) w[k] += Wc[6 * i + k];
+        if (b1 == b) for (int k = 0; k < 6; k++) w[k] -= Wc[6 * i + k];
       }
     for (int k = 0; k < 6; k++) Wb[6 * b + k] = w[k];
   }

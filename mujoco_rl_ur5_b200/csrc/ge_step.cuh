@@ -31,9 +31,6 @@ __device__ __noinline__ StepInfo forward(double* ws, int* wi, int lane, int* sta
   stage_fk(ws, lane);
   stage_rne(ws, lane);  // qfrc_smooth := bias
   stage_crb(ws, lane);
-  LANE_LOOP(i, m.nM) ws[L.qLD + i] = ws[L.qM + i];
-  __syncwarp();
-  factor_trees(ws + L.qLD, lane);
   stage_barrier(sync);
   si.ncon = stage_collision(ws, wi, lane, status);
   // smooth forces: passive (joint damping) - bias + actuation (torque motors, gear * clamp(ctrl))
@@ -49,7 +46,14 @@ __device__ __noinline__ StepInfo forward(double* ws, int* wi, int lane, int* sta
   __syncwarp();
   LANE_LOOP(d, m.nv) qas[d] = qfs[d];
   __syncwarp();
-  solve_trees(ws + L.qLD, qas, lane);
+  // qacc_smooth = M^-1 qfrc_smooth: dense per-tree Cholesky in 8-lane groups (Hessian storage is free here); models with a
+  // tree wider than a lane group fall back to the tree-sparse L^T D L factorisation
+  if (!mass_block_solve(ws, qas, 0.0, lane)) {
+    LANE_LOOP(i, m.nM) ws[L.qLD + i] = ws[L.qM + i];
+    __syncwarp();
+    factor_trees(ws + L.qLD, lane);
+    solve_trees(ws + L.qLD, qas, lane);
+  }
   stage_barrier(sync);
   si.nsr = stage_constraints(ws, wi, lane, si.ncon, status);
   si.niter = solve_newton(ws, wi, lane, si.ncon, si.nsr);
@@ -67,15 +71,18 @@ __device__ __noinline__ StepInfo sim_step(double* ws, int* wi, int lane, int* st
   double h = m.timestep;
   double *acc = ws + L.grad, *qH = ws + L.qLD, *qvel = ws + L.qvel, *qpos = ws + L.qpos;
   LANE_LOOP(d, m.nv) acc[d] = ws[L.qfrc_smooth + d] + ws[L.qfrc_constraint + d];
-  if (m.any_damping) {
-    LANE_LOOP(i, m.nM) qH[i] = ws[L.qM + i];
-    __syncwarp();
-    LANE_LOOP(d, m.nv) qH[m.dof_Madr[d]] += h * m.dof_damping[d];
-    __syncwarp();
-    factor_trees(qH, lane);
-  }
   __syncwarp();
-  solve_trees(qH, acc, lane);
+  if (!mass_block_solve(ws, acc, m.any_damping ? h : 0.0, lane)) {
+    if (m.any_damping) {
+      LANE_LOOP(i, m.nM) qH[i] = ws[L.qM + i];
+      __syncwarp();
+      LANE_LOOP(d, m.nv) qH[m.dof_Madr[d]] += h * m.dof_damping[d];
+      __syncwarp();
+      factor_trees(qH, lane);
+    }
+    __syncwarp();
+    solve_trees(qH, acc, lane);
+  }
   LANE_LOOP(d, m.nv) qvel[d] += h * acc[d];
   __syncwarp();
   bool bad = false;

@@ -309,7 +309,7 @@ static void make_layout(const DevModel& m, Layout& L) {
   L.total_doubles = align_up(end, 2);
   int io = 0;
   auto takeI = [&](int n) { int r = io; io += n; return r; };
-  L.i_cb1 = takeI(GE_MAXCON); L.i_cb2 = takeI(GE_MAXCON); L.i_cdim = takeI(GE_MAXCON); L.i_cpair = takeI(GE_MAXCON); L.i_cact = takeI(GE_MAXCON);
+  L.i_cb1 = takeI(GE_MAXCON); L.i_cb2 = takeI(GE_MAXCON); L.i_ct1 = takeI(GE_MAXCON); L.i_ct2 = takeI(GE_MAXCON); L.i_cdim = takeI(GE_MAXCON); L.i_cpair = takeI(GE_MAXCON); L.i_cact = takeI(GE_MAXCON);
   L.i_srA = takeI(GE_MAXSR); L.i_srB = takeI(GE_MAXSR); L.i_srtype = takeI(GE_MAXSR); L.i_sract = takeI(GE_MAXSR);
   L.i_cand = takeI(GE_MAXCAND); L.i_first = takeI(nv); L.i_tcoupled = takeI(m.ntree); L.i_misc = takeI(8);
   L.total_ints = align_up(io, 4);
@@ -342,7 +342,7 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
   m.qpos0 = PD("qpos0"); m.body_pos = PD("body_pos"); m.body_quat = PD("body_quat"); m.body_mass = PD("body_mass"); m.body_ipos = PD("body_ipos");
   m.body_inertia = PD("body_inertia"); m.body_invweight0 = PD("body_invweight0");
   m.body_parentid = PI("body_parentid"); m.body_jntadr = PI("body_jntadr"); m.body_jntnum = PI("body_jntnum"); m.body_lastdof = PI("body_lastdof");
-  m.body_subtreenum = PI("body_subtreenum");
+  m.body_subtreenum = PI("body_subtreenum"); m.body_chainmask = PI("body_chainmask");
   m.jnt_type = PI("jnt_type"); m.jnt_bodyid = PI("jnt_bodyid"); m.jnt_qposadr = PI("jnt_qposadr"); m.jnt_dofadr = PI("jnt_dofadr"); m.jnt_limited = PI("jnt_limited");
   m.jnt_pos = PD("jnt_pos"); m.jnt_axis = PD("jnt_axis"); m.jnt_range = PD("jnt_range"); m.jnt_margin = PD("jnt_margin"); m.jnt_solref = PD("jnt_solref"); m.jnt_solimp = PD("jnt_solimp");
   m.dof_bodyid = PI("dof_bodyid"); m.dof_jntid = PI("dof_jntid"); m.dof_parentid = PI("dof_parentid"); m.dof_Madr = PI("dof_Madr");

@@ -30,9 +30,10 @@ def load_library():
     """Load the CUDA engine; raises EngineError (never falls back) if it has not been built."""
     global _LIB
     if _LIB is None:
-        if not os.path.exists(LIB_PATH):
-            raise EngineError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
-        L = C.CDLL(LIB_PATH)
+        path = os.environ.get("GE_LIB", LIB_PATH)  # GE_LIB: alternative build of the same library (kernel experiments)
+        if not os.path.exists(path):
+            raise EngineError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(path)
         P = C.c_void_p
         L.ge_last_error.restype = C.c_char_p
         L.ge_version.restype = C.c_char_p

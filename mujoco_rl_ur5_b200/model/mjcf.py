@@ -462,6 +462,16 @@ def compile_mjcf(path):
     M["dof_subtreenum"] = dof_subtreenum
     M["dof_depth"] = dof_depth
     M["dof_treeindex"] = np.array([tree_roots.index(int(dof_tree[d])) for d in range(nv)], np.int32)
+    # per body: bit l set <=> tree-local dof l (dof - root of its tree) lies on the path world -> body (trees of <= 32 dofs)
+    chainmask = np.zeros(nbody, np.int64)
+    for bid in range(nbody):
+        d = body_lastdof[bid]
+        while d >= 0:
+            loc = d - int(dof_tree[d])
+            if loc < 31:
+                chainmask[bid] |= 1 << loc
+            d = dof_parent[d]
+    M["body_chainmask"] = chainmask.astype(np.int32)
     M["tree_dofadr"] = np.array(tree_roots, np.int32)
     M["tree_dofnum"] = np.array([dof_subtreenum[d] for d in tree_roots], np.int32)
     M["ntree"] = len(tree_roots)
