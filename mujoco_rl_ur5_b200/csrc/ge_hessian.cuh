@@ -8,6 +8,7 @@
 #pragma once
 
 #define HIDX(i, j) (((i) * ((i) + 1)) / 2 + (j))
+#define GE_TLIST 16  // contacts per uncoupled tree handled by the group path (more -> the tree takes the coupled path)
 #define GE_GROUP 8  // lanes per kinematic tree in the uncoupled-tree path (trees with more dofs use the coupled path)
 
 namespace ge {
@@ -67,36 +68,51 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
     first[i] = root;
   }
   __syncwarp();
-  // ---- uncoupled trees: one 8-lane group per tree (4 trees at a time); lane l of the group owns dof lo + l.
-  // For every active contact that lives inside the tree the group rebuilds its Jacobian block in registers and adds
-  // J^T W J to the tree's dense block with width-8 shuffles.  Groups run in lock-step but never touch each other's rows.
+  // ---- per-tree lists of the active contacts that live entirely inside one uncoupled tree (one lane per tree scans the contacts)
+  int *tcount = wi + L.i_tcount, *tlist = wi + L.i_tlist;
+  LANE_LOOP(t, m.ntree) {
+    int cnt = 0;
+    if (!tcoupled[t]) {
+      for (int ci = 0; ci < ncon; ci++)
+        if (wi[L.i_cact + ci] && (wi[L.i_ct1 + ci] == t || wi[L.i_ct2 + ci] == t)) { if (cnt < GE_TLIST) tlist[t * GE_TLIST + cnt] = ci; cnt++; }
+      if (cnt > GE_TLIST) { tcoupled[t] = 1; cnt = 0; }  // too many contacts for the list: this tree takes the coupled path
+    }
+    tcount[t] = cnt;
+  }
+  __syncwarp();
+  // ---- uncoupled trees: one 8-lane group per tree, 4 trees at a time, every group walking ITS OWN contact list so that the four
+  // groups really run concurrently (same instruction stream, different contacts).  Lane l of a group owns dof lo + l; the
+  // contact's Jacobian block is rebuilt in registers and J^T W J is added to the tree's dense block through shuffles.
   {
     const int g = lane / GE_GROUP, l = lane % GE_GROUP;
-    const unsigned gmask = ((1u << GE_GROUP) - 1u) << (g * GE_GROUP);
     for (int t0 = 0; t0 < m.ntree; t0 += 32 / GE_GROUP) {
-      int t = t0 + g;
-      if (t >= m.ntree || tcoupled[t]) continue;  // group-uniform
-      int lo = m.tree_dofadr[t], nt = m.tree_dofnum[t], mydof = l < nt ? lo + l : -1;
-      for (int ci = 0; ci < ncon; ci++) {
-        int mask = wi[L.i_cact + ci];
-        if (!mask) continue;
-        int t1 = wi[L.i_ct1 + ci], t2 = wi[L.i_ct2 + ci];
-        if (t1 != t && t2 != t) continue;
-        const double* c = ws + L.con + ci * L.cstride;
-        int dim = wi[L.i_cdim + ci];
-        // sign of my dof in the contact's dof list (chains of both bodies minus their common ancestors), from the per-body
-        // bit masks over the tree-local dof index
-        unsigned m1 = t1 == t ? (unsigned)m.body_chainmask[wi[L.i_cb1 + ci]] : 0u, m2 = t2 == t ? (unsigned)m.body_chainmask[wi[L.i_cb2 + ci]] : 0u;
-        double sgn = ((m2 & ~m1) >> l & 1u) ? 1.0 : (((m1 & ~m2) >> l & 1u) ? -1.0 : 0.0);
+      const int t = t0 + g;
+      const bool valid = t < m.ntree && !tcoupled[t];
+      const int lo = valid ? m.tree_dofadr[t] : 0, nt = valid ? m.tree_dofnum[t] : 0, cnt = valid ? tcount[t] : 0;
+      const int mydof = lo + l;
+      int maxcnt = cnt;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(FULL, maxcnt, o));
+      for (int n = 0; n < maxcnt; n++) {
+        const bool act = n < cnt && l < nt;
         double J[6] = {0, 0, 0, 0, 0, 0}, tw[6] = {0, 0, 0, 0, 0, 0};
-        if (sgn != 0) { jac_column(c, dim, cdof + 6 * mydof, sgn, J); weight_column(c, dim, mask, J, tw); }
-        for (int f = 0; f < nt; f++) {
+        if (act) {
+          const int ci = tlist[t * GE_TLIST + n];
+          const double* c = ws + L.con + ci * L.cstride;
+          const int dim = wi[L.i_cdim + ci], t1 = wi[L.i_ct1 + ci], t2 = wi[L.i_ct2 + ci];
+          // sign of my dof in the contact's dof list (chains of both bodies minus their common ancestors) from the per-body
+          // bit masks over the tree-local dof index
+          unsigned m1 = t1 == t ? (unsigned)m.body_chainmask[wi[L.i_cb1 + ci]] : 0u, m2 = t2 == t ? (unsigned)m.body_chainmask[wi[L.i_cb2 + ci]] : 0u;
+          double sgn = ((m2 & ~m1) >> l & 1u) ? 1.0 : (((m1 & ~m2) >> l & 1u) ? -1.0 : 0.0);
+          if (sgn != 0) { jac_column(c, dim, cdof + 6 * mydof, sgn, J); weight_column(c, dim, wi[L.i_cact + ci], J, tw); }
+        }
+        for (int f = 0; f < GE_GROUP; f++) {
           double h = 0;
-          for (int k = 0; k < dim; k++) h += tw[k] * __shfl_sync(gmask, J[k], f, GE_GROUP);
-          if (l >= f && l < nt && h != 0.0) H[HIDX(lo + l, lo + f)] += h;
+          for (int k = 0; k < m.maxdim; k++) h += tw[k] * __shfl_sync(FULL, J[k], g * GE_GROUP + f);
+          if (act && l >= f && f < nt && h != 0.0) H[HIDX(lo + l, lo + f)] += h;
         }
       }
-      if (l == 0)
+      if (valid && l == 0)
         for (int i = 0; i < nsr; i++) {
           if (!wi[L.i_sract + i]) continue;
           int A = wi[L.i_srA + i], B = wi[L.i_srB + i];
@@ -109,6 +125,7 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
             H[HIDX(hi, lw)] += D * ca * cb;
           }
         }
+      __syncwarp();
     }
   }
   __syncwarp();
@@ -230,10 +247,29 @@ __device__ __forceinline__ void group_chol_solve(double* H, int lo, int nt, int 
 // a lane group; returns false (nothing done) otherwise so that the caller can fall back.
 __device__ __noinline__ bool mass_block_solve(double* ws, double* x, double hdamp, int lane) {
   const DevModel& m = c_m; const Layout& L = c_L;
-  for (int t = 0; t < m.ntree; t++) if (m.tree_dofnum[t] > GE_GROUP) return false;
+  for (int t = 0; t < m.ntree; t++) if (m.tree_dofnum[t] > GE_GROUP && !m.tree_simple[t]) return false;
   double* H = ws + L.H;
   const double* qM = ws + L.qM;
+  // "simple" trees (free-floating single bodies): the block is a model constant, multiply by the precomputed inverse
+  // (tree_Minv[t][0] = M^-1, [1] = (M + h*damping)^-1 for h = opt.timestep); rows are read before any is written
+  const int which = hdamp != 0.0 ? 1 : 0;
+  double xs[2] = {0, 0};
+  {
+    int n = 0;
+    LANE_LOOP(i, m.nv) {
+      int t = m.dof_treeindex[i];
+      if (m.tree_simple[t]) {
+        int lo = m.tree_dofadr[t];
+        const double* Mi = m.tree_Minv + ((size_t)(t * 2 + which) * 6 + (i - lo)) * 6;
+        double s = 0;
+        for (int j = 0; j < 6; j++) s += Mi[j] * x[lo + j];
+        xs[n] = s;
+      }
+      n++;
+    }
+  }
   LANE_LOOP(i, m.nv) {
+    if (m.tree_simple[m.dof_treeindex[i]]) continue;
     int root = m.tree_dofadr[m.dof_treeindex[i]];
     for (int j = root; j <= i; j++) H[HIDX(i, j)] = 0;
     int a = m.dof_Madr[i], k = 0;
@@ -241,12 +277,18 @@ __device__ __noinline__ bool mass_block_solve(double* ws, double* x, double hdam
     if (hdamp != 0.0) H[HIDX(i, i)] += hdamp * m.dof_damping[i];
   }
   __syncwarp();
+  {
+    int n = 0;
+    LANE_LOOP(i, m.nv) { if (m.tree_simple[m.dof_treeindex[i]]) x[i] = xs[n]; n++; }
+  }
   const int g = lane / GE_GROUP, l = lane % GE_GROUP;
   const unsigned gmask = ((1u << GE_GROUP) - 1u) << (g * GE_GROUP);
-  for (int t0 = 0; t0 < m.ntree; t0 += 32 / GE_GROUP) {
-    int t = t0 + g;
-    if (t >= m.ntree) continue;
-    group_chol_solve(H, m.tree_dofadr[t], m.tree_dofnum[t], l, gmask, x, x, 1.0);
+  // the remaining trees, packed four at a time onto the lane groups
+  int slot = 0;
+  for (int t = 0; t < m.ntree; t++) {
+    if (m.tree_simple[t]) continue;
+    if (slot % (32 / GE_GROUP) == g) group_chol_solve(H, m.tree_dofadr[t], m.tree_dofnum[t], l, gmask, x, x, 1.0);
+    slot++;
   }
   __syncwarp();
   return true;

@@ -21,8 +21,8 @@ struct DevModel {
   const int *body_parentid, *body_jntadr, *body_jntnum, *body_lastdof, *body_subtreenum, *body_chainmask;
   const int *jnt_type, *jnt_bodyid, *jnt_qposadr, *jnt_dofadr, *jnt_limited;
   const double *jnt_pos, *jnt_axis, *jnt_range, *jnt_margin, *jnt_solref, *jnt_solimp;
-  const int *dof_bodyid, *dof_jntid, *dof_parentid, *dof_Madr, *dof_subtreenum, *dof_depth, *dof_treeindex, *tree_dofadr, *tree_dofnum;
-  const double *dof_armature, *dof_damping, *dof_invweight0;
+  const int *dof_bodyid, *dof_jntid, *dof_parentid, *dof_Madr, *dof_subtreenum, *dof_depth, *dof_treeindex, *tree_dofadr, *tree_dofnum, *tree_simple;
+  const double *dof_armature, *dof_damping, *dof_invweight0, *tree_Minv;
   const int *geom_type, *geom_bodyid, *geom_meshid;
   const double *geom_pos, *geom_lmat, *geom_size, *geom_rbound, *geom_obbcenter, *geom_obbhalf, *geom_rgba;
   const int *mesh_vertadr, *mesh_vertnum, *mesh_faceadr, *mesh_facenum;
@@ -52,7 +52,7 @@ struct Layout {
   // --- aliases inside scratch: solver phase
   int H, Vb, Wb;
   // --- ints
-  int i_cb1, i_cb2, i_ct1, i_ct2, i_cdim, i_cpair, i_cact, i_srA, i_srB, i_srtype, i_sract, i_cand, i_first, i_tcoupled, i_misc;
+  int i_cb1, i_cb2, i_ct1, i_ct2, i_cdim, i_cpair, i_cact, i_srA, i_srB, i_srtype, i_sract, i_cand, i_first, i_tcoupled, i_tcount, i_tlist, i_misc;
   int total_ints;
   int total_bytes;
 };

@@ -311,7 +311,7 @@ static void make_layout(const DevModel& m, Layout& L) {
   auto takeI = [&](int n) { int r = io; io += n; return r; };
   L.i_cb1 = takeI(GE_MAXCON); L.i_cb2 = takeI(GE_MAXCON); L.i_ct1 = takeI(GE_MAXCON); L.i_ct2 = takeI(GE_MAXCON); L.i_cdim = takeI(GE_MAXCON); L.i_cpair = takeI(GE_MAXCON); L.i_cact = takeI(GE_MAXCON);
   L.i_srA = takeI(GE_MAXSR); L.i_srB = takeI(GE_MAXSR); L.i_srtype = takeI(GE_MAXSR); L.i_sract = takeI(GE_MAXSR);
-  L.i_cand = takeI(GE_MAXCAND); L.i_first = takeI(nv); L.i_tcoupled = takeI(m.ntree); L.i_misc = takeI(8);
+  L.i_cand = takeI(GE_MAXCAND); L.i_first = takeI(nv); L.i_tcoupled = takeI(m.ntree); L.i_tcount = takeI(m.ntree); L.i_tlist = takeI(m.ntree * 16); L.i_misc = takeI(8);
   L.total_ints = align_up(io, 4);
   L.total_bytes = L.total_doubles * 8 + L.total_ints * 4;
 }
@@ -346,7 +346,7 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
   m.jnt_type = PI("jnt_type"); m.jnt_bodyid = PI("jnt_bodyid"); m.jnt_qposadr = PI("jnt_qposadr"); m.jnt_dofadr = PI("jnt_dofadr"); m.jnt_limited = PI("jnt_limited");
   m.jnt_pos = PD("jnt_pos"); m.jnt_axis = PD("jnt_axis"); m.jnt_range = PD("jnt_range"); m.jnt_margin = PD("jnt_margin"); m.jnt_solref = PD("jnt_solref"); m.jnt_solimp = PD("jnt_solimp");
   m.dof_bodyid = PI("dof_bodyid"); m.dof_jntid = PI("dof_jntid"); m.dof_parentid = PI("dof_parentid"); m.dof_Madr = PI("dof_Madr");
-  m.dof_subtreenum = PI("dof_subtreenum"); m.dof_depth = PI("dof_depth"); m.dof_treeindex = PI("dof_treeindex"); m.tree_dofadr = PI("tree_dofadr"); m.tree_dofnum = PI("tree_dofnum");
+  m.dof_subtreenum = PI("dof_subtreenum"); m.dof_depth = PI("dof_depth"); m.dof_treeindex = PI("dof_treeindex"); m.tree_dofadr = PI("tree_dofadr"); m.tree_dofnum = PI("tree_dofnum"); m.tree_simple = PI("tree_simple"); m.tree_Minv = PD("tree_Minv");
   m.dof_armature = PD("dof_armature"); m.dof_damping = PD("dof_damping"); m.dof_invweight0 = PD("dof_invweight0");
   m.geom_type = PI("geom_type"); m.geom_bodyid = PI("geom_bodyid"); m.geom_meshid = PI("geom_meshid");
   m.geom_pos = PD("geom_pos"); m.geom_lmat = PD("geom_lmat"); m.geom_size = PD("geom_size"); m.geom_rbound = PD("geom_rbound");

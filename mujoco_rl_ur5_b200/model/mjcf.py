@@ -506,6 +506,40 @@ def compile_mjcf(path):
         A = Jp @ Minv @ Jp.T
         B = Jr @ Minv @ Jr.T
         body_inv[bid] = [np.trace(A) / 3, np.trace(B) / 3]
+    # "simple" trees: a single free-floating body (3 world slides + ball, or one free joint) whose centre of mass sits on the joint
+    # anchor.  Their mass-matrix block does not depend on the configuration (m*1 (+) I_body, + armature), so (M)^-1 and
+    # (M + h*damping)^-1 are model constants: the sub-step kernel multiplies by them instead of factorising (tree_Minv[t,0|1,6,6]).
+    ntree = len(tree_roots)
+    tree_simple = np.zeros(ntree, np.int32)
+    tree_Minv = np.zeros((ntree, 2, 6, 6))
+    hstep = float(opt.get("timestep", 0.002))
+    rng_chk = np.random.RandomState(0)
+    for t, r in enumerate(tree_roots):
+        n = int(dof_subtreenum[r])
+        bset = sorted(set(int(dof_body[d]) for d in range(r, r + n)))
+        if n != 6 or len(bset) != 1:
+            continue
+        # numerical check of configuration independence: M block at qpos0 vs at a random configuration
+        q2 = qpos0.copy()
+        for j in bodies[bset[0]]["joints"]:
+            jt, qa = joints[j]["type"], joints[j]["qadr"]
+            if jt in (J_SLIDE, J_HINGE):
+                q2[qa] += rng_chk.uniform(-0.3, 0.3)
+            else:
+                if jt == J_FREE:
+                    q2[qa:qa + 3] += rng_chk.uniform(-0.3, 0.3, 3)
+                    qa += 3
+                qq = rng_chk.normal(size=4)
+                q2[qa:qa + 4] = qq / np.linalg.norm(qq)
+        B0 = Mq[r:r + 6, r:r + 6]
+        B1 = kin.mass_matrix(q2)[r:r + 6, r:r + 6]
+        if np.abs(B0 - B1).max() > 1e-13 * max(1.0, np.abs(B0).max()):
+            continue
+        tree_simple[t] = 1
+        tree_Minv[t, 0] = np.linalg.inv(B0)
+        tree_Minv[t, 1] = np.linalg.inv(B0 + hstep * np.diag(dof_damp[r:r + 6]))
+    M["tree_simple"] = tree_simple
+    M["tree_Minv"] = tree_Minv
     M["dof_invweight0"] = dof_inv
     M["body_invweight0"] = body_inv
     M["stat_meaninertia"] = float(np.trace(Mq) / max(nv, 1))
