@@ -27,8 +27,8 @@ struct DevModel {
   const double *geom_pos, *geom_lmat, *geom_size, *geom_rbound, *geom_obbcenter, *geom_obbhalf, *geom_rgba;
   const int *mesh_vertadr, *mesh_vertnum, *mesh_faceadr, *mesh_facenum;
   const double *mesh_vert, *mesh_center, *mesh_faceplane;
-  const int *pair_geom, *pair_condim;
-  const double *pair_friction, *pair_margin, *pair_solref, *pair_solimp;
+  const int *pair_geom, *pair_condim, *pair_rec;
+  const double *pair_friction, *pair_margin, *pair_solref, *pair_solimp, *pair_rsum;
   const int* actuator_jntid;
   const double *actuator_gear, *actuator_ctrlrange;
   const int *eq_jnt1, *eq_jnt2;
@@ -47,7 +47,7 @@ struct Layout {
   int scratch;                  // phase-aliased region, see below
   int total_doubles;
   // --- aliases inside scratch: kinematics / dynamics phase
-  int lpos, lquat, janchor, jaxis, xpos, xquat, xmat, xipos, cinert, gpos, gmat;  // FK phase
+  int lpos, lquat, janchor, jaxis, xpos, xquat, xmat, xipos, cinert, gpos, gmat, gcen;  // FK phase
   int cvel, cacc, cfrc, cdofdot;                                                   // RNE phase (over lpos.. janchor.. xpos..)
   // --- aliases inside scratch: solver phase
   int H, Vb, Wb;

@@ -113,6 +113,7 @@ __device__ __noinline__ void stage_fk(double* ws, int lane) {
     double t[3];
     m3mulv(t, xmat + 9 * b, m.geom_pos + 3 * g); v3add(gpos + 3 * g, xpos + 3 * b, t);
     m3mul(gmat + 9 * g, xmat + 9 * b, m.geom_lmat + 9 * g);
+    m3mulv(t, gmat + 9 * g, m.geom_obbcenter + 3 * g); v3add(ws + L.gcen + 3 * g, gpos + 3 * g, t);  // bounding-sphere / OBB centre
   }
   __syncwarp();
 }
@@ -350,8 +351,9 @@ __device__ __noinline__ void col_sphere_box(const double* ws, int g1, int g2, do
   out.dist[0] = dist; out.n = 1;
 }
 
-__device__ __forceinline__ int clip_poly(const double (*p)[2], int n, int axis, double lim, double (*out)[2]) {
+__device__ __noinline__ int clip_poly(const double (*p)[2], int n, int axis, double lim, double (*out)[2]) {
   int k = 0;
+  #pragma unroll 1
   for (int i = 0; i < n; i++) {
     const double *a = p[i], *b = p[(i + 1 == n) ? 0 : i + 1];
     double da = a[axis] - lim, db = b[axis] - lim;
@@ -367,20 +369,25 @@ __device__ __noinline__ void col_box_box(const double* ws, int g1, int g2, doubl
   const double *h1 = m.geom_size + 3 * g1, *h2 = m.geom_size + 3 * g2;
   double d[3], a[3][3], b[3][3], C[3][3], AC[3][3];
   v3sub(d, c2, c1);
+  #pragma unroll 1
   for (int i = 0; i < 3; i++) { m3col(a[i], R1, i); m3col(b[i], R2, i); }
+  #pragma unroll 1
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { C[i][j] = v3dot(a[i], b[j]); AC[i][j] = fabs(C[i][j]); }
   double best_s = -1e300; int best_axis = -1;
+  #pragma unroll 1
   for (int i = 0; i < 3; i++) {
     double s = fabs(v3dot(d, a[i])) - (h1[i] + h2[0] * AC[i][0] + h2[1] * AC[i][1] + h2[2] * AC[i][2]);
     if (s >= margin) return;
     if (s > best_s) { best_s = s; best_axis = i; }
   }
+  #pragma unroll 1
   for (int j = 0; j < 3; j++) {
     double s = fabs(v3dot(d, b[j])) - (h2[j] + h1[0] * AC[0][j] + h1[1] * AC[1][j] + h1[2] * AC[2][j]);
     if (s >= margin) return;
     if (s > best_s) { best_s = s; best_axis = 3 + j; }
   }
   double edge_s = -1e300; int ei = -1, ej = -1; double en[3] = {0, 0, 0};
+  #pragma unroll 1
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
     double Lx[3];
     v3cross(Lx, a[i], b[j]);
@@ -388,6 +395,7 @@ __device__ __noinline__ void col_box_box(const double* ws, int g1, int g2, doubl
     if (len < 1e-6) continue;
     v3scl(Lx, Lx, 1.0 / len);
     double ra = 0, rb = 0;
+    #pragma unroll 1
     for (int k = 0; k < 3; k++) { ra += h1[k] * fabs(v3dot(Lx, a[k])); rb += h2[k] * fabs(v3dot(Lx, b[k])); }
     double s = fabs(v3dot(d, Lx)) - ra - rb;
     if (s >= margin) return;
@@ -398,6 +406,7 @@ __device__ __noinline__ void col_box_box(const double* ws, int g1, int g2, doubl
     v3copy(n, en);
     if (v3dot(d, n) < 0) v3scl(n, n, -1.0);
     v3copy(p1, c1); v3copy(p2, c2);
+    #pragma unroll 1
     for (int k = 0; k < 3; k++) {
       if (k != ei) v3addscl(p1, p1, a[k], (v3dot(n, a[k]) >= 0 ? 1.0 : -1.0) * h1[k]);
       if (k != ej) v3addscl(p2, p2, b[k], (v3dot(n, b[k]) >= 0 ? -1.0 : 1.0) * h2[k]);
@@ -424,6 +433,7 @@ __device__ __noinline__ void col_box_box(const double* ws, int g1, int g2, doubl
   v3sub(dr, ci, cr);
   v3scl(nref, ar[ax], v3dot(dr, ar[ax]) >= 0 ? 1.0 : -1.0);
   int inc = 0; double bestd = -1;
+  #pragma unroll 1
   for (int k = 0; k < 3; k++) { double s = fabs(v3dot(ai[k], nref)); if (s > bestd) { bestd = s; inc = k; } }
   double sgn = v3dot(ai[inc], nref) > 0 ? -1.0 : 1.0;
   double fc[3];
@@ -431,6 +441,7 @@ __device__ __noinline__ void col_box_box(const double* ws, int g1, int g2, doubl
   int u1 = (inc + 1) % 3, u2 = (inc + 2) % 3, r1 = (ax + 1) % 3, r2 = (ax + 2) % 3;
   double poly[16][2], tmp[16][2], height[4];
   const double sg[4][2] = {{1, 1}, {-1, 1}, {-1, -1}, {1, -1}};
+  #pragma unroll 1
   for (int k = 0; k < 4; k++) {
     double corner[3], rel[3];
     v3addscl(corner, fc, ai[u1], sg[k][0] * hi[u1]); v3addscl(corner, corner, ai[u2], sg[k][1] * hi[u2]);
@@ -447,14 +458,19 @@ __device__ __noinline__ void col_box_box(const double* ws, int g1, int g2, doubl
   double g0 = height[0] - gx * poly[0][0] - gy * poly[0][1];
   int n = 4;
   n = clip_poly(poly, n, 0, hr[r1], tmp); if (!n) return;
+  #pragma unroll 1
   for (int k = 0; k < n; k++) tmp[k][0] = -tmp[k][0];
   n = clip_poly(tmp, n, 0, hr[r1], poly); if (!n) return;
+  #pragma unroll 1
   for (int k = 0; k < n; k++) poly[k][0] = -poly[k][0];
   n = clip_poly(poly, n, 1, hr[r2], tmp); if (!n) return;
+  #pragma unroll 1
   for (int k = 0; k < n; k++) tmp[k][1] = -tmp[k][1];
   n = clip_poly(tmp, n, 1, hr[r2], poly); if (!n) return;
+  #pragma unroll 1
   for (int k = 0; k < n; k++) poly[k][1] = -poly[k][1];
   v3scl(out.normal, nref, ref1 ? 1.0 : -1.0);
+  #pragma unroll 1
   for (int k = 0; k < n && out.n < 8; k++) {
     double dist = g0 + gx * poly[k][0] + gy * poly[k][1];
     if (dist >= margin) continue;
@@ -485,9 +501,21 @@ __device__ __noinline__ void support_w(const double* ws, int g, double inflate, 
     int k = m.geom_meshid[g], nvert = m.mesh_vertnum[k], best = 0x7fffffff;
     const double* v = m.mesh_vert + 3 * m.mesh_vertadr[k];
     double bv = -1e300;
-    for (int i = lane; i < nvert; i += 32) {
-      double t = __ldg(v + 3 * i) * dl[0] + __ldg(v + 3 * i + 1) * dl[1] + __ldg(v + 3 * i + 2) * dl[2];
-      if (t > bv) { bv = t; best = i; }
+    // four vertices per lane and trip: 12 independent loads in flight before the (ordered) comparisons
+    for (int i0 = lane; i0 < nvert; i0 += 128) {
+      double c[4][3];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        int i = i0 + 32 * u;
+        bool ok = i < nvert;
+        c[u][0] = ok ? __ldg(v + 3 * i) : 0.0; c[u][1] = ok ? __ldg(v + 3 * i + 1) : 0.0; c[u][2] = ok ? __ldg(v + 3 * i + 2) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        int i = i0 + 32 * u;
+        double t = c[u][0] * dl[0] + c[u][1] * dl[1] + c[u][2] * dl[2];
+        if (i < nvert && t > bv) { bv = t; best = i; }
+      }
     }
     warp_argmax(bv, best);
     v3copy(pl, v + 3 * best);
@@ -604,28 +632,30 @@ __device__ __forceinline__ void make_frame(double* fr) {
 // bit 0 of *status on overflow.  (The oracle emits contacts in the same order: analytic pairs first, then MPR pairs.)
 __device__ __noinline__ int stage_collision(double* ws, int* wi, int lane, int* status) {
   const DevModel& m = c_m; const Layout& L = c_L;
-  const double *gpos = ws + L.gpos, *gmat = ws + L.gmat;
+  const double *gpos = ws + L.gpos, *gmat = ws + L.gmat, *gcen = ws + L.gcen;
   int* cand = wi + L.i_cand;
   int ncand = 0;
   for (int base = 0; base < m.npair; base += 32) {
     int p = base + lane;
     bool pass = false;
     if (p < m.npair) {
-      int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1], t1 = m.geom_type[g1], t2 = m.geom_type[g2];
-      double margin = m.pair_margin[p], c1[3], c2[3], t[3];
-      m3mulv(t, gmat + 9 * g2, m.geom_obbcenter + 3 * g2); v3add(c2, gpos + 3 * g2, t);
+      // one 16-byte record per pair (geom ids + types) and the precomputed sum of bounding radii + margin; the world-space
+      // bounding-sphere centres of all geoms were computed once in stage_fk (gcen)
+      const int4 pr = __ldg((const int4*)m.pair_rec + p);
+      const int g1 = pr.x, g2 = pr.y, t1 = pr.z, t2 = pr.w;
+      const double rs = __ldg(m.pair_rsum + p);
+      const double* c2 = gcen + 3 * g2;
       if (t1 == G_PLANE) {
         double n[3], d[3];
         m3col(n, gmat + 9 * g1, 2); v3sub(d, c2, gpos + 3 * g1);
-        pass = !(v3dot(d, n) > m.geom_rbound[g2] + margin);
+        pass = !(v3dot(d, n) > rs);
       } else {
-        m3mulv(t, gmat + 9 * g1, m.geom_obbcenter + 3 * g1); v3add(c1, gpos + 3 * g1, t);
+        const double* c1 = gcen + 3 * g1;
         double d[3];
         v3sub(d, c2, c1);
-        double rs = m.geom_rbound[g1] + m.geom_rbound[g2] + margin;
         pass = !(v3dot(d, d) > rs * rs);
         if (pass && !(t1 == G_SPHERE && t2 == G_SPHERE))
-          pass = !obb_separated(c1, gmat + 9 * g1, m.geom_obbhalf + 3 * g1, c2, gmat + 9 * g2, m.geom_obbhalf + 3 * g2, margin);
+          pass = !obb_separated(c1, gmat + 9 * g1, m.geom_obbhalf + 3 * g1, c2, gmat + 9 * g2, m.geom_obbhalf + 3 * g2, m.pair_margin[p]);
       }
     }
     unsigned mask = __ballot_sync(FULL, pass);

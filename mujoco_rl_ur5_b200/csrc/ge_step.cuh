@@ -22,7 +22,7 @@ struct StepInfo { int ncon, nsr, niter; };
 #endif
 #define GE_NUM_STAGE_BARRIERS 3
 __device__ __forceinline__ void stage_barrier(bool sync) { if (GE_STAGE_SYNC && sync) __syncthreads(); }
-__device__ __forceinline__ void stage_barriers_idle() { if (GE_STAGE_SYNC) for (int k = 0; k < GE_NUM_STAGE_BARRIERS; k++) __syncthreads(); }
+__device__ __forceinline__ void stage_barriers_idle(bool on) { if (GE_STAGE_SYNC && on) for (int k = 0; k < GE_NUM_STAGE_BARRIERS; k++) __syncthreads(); }
 
 // mj_forward: kinematics -> bias -> mass matrix -> collision -> constraints -> smooth acceleration -> Newton
 __device__ __noinline__ StepInfo forward(double* ws, int* wi, int lane, int* status, bool sync = false) {

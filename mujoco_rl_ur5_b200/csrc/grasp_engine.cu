@@ -28,7 +28,7 @@ extern "C" const char* ge_version(void) { return "grasp_engine 0.1 sm_100a fp64 
 // iterations of the reference control loop (PID -> mj_step) including movement / grasp-program transitions, writes back.
 // A CTA holds `blockDim.y` warps (= environments); they meet at one barrier per sub-step so that the warps of an SM walk the
 // (large) sub-step code roughly together and share instruction-cache lines.
-__global__ void __launch_bounds__(256) k_run(EnvArrays E, int n_env, int nsub, double base_x, double base_y, double base_z) {
+__global__ void __launch_bounds__(256) k_run(EnvArrays E, int n_env, int nsub, double base_x, double base_y, double base_z, int stage_sync) {
   extern __shared__ double smem[];
   const DevModel& m = c_m; const Layout& L = c_L;
   int env = blockIdx.x * blockDim.y + threadIdx.y, lane = threadIdx.x;
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) k_run(EnvArrays E, int n_env, int nsub, d
   bool running = busy;
   for (int it = 0; it < nsub; it++) {
     if (!__syncthreads_or(running)) break;
-    if (!running) { stage_barriers_idle(); continue; }
+    if (!running) { stage_barriers_idle(stage_sync != 0); continue; }
     bool stepped = false;
     // one iteration of the reference loop that ends in a physics step (or the env going idle)
     while (true) {
@@ -74,13 +74,13 @@ __global__ void __launch_bounds__(256) k_run(EnvArrays E, int n_env, int nsub, d
       double delta = pid_and_delta(ws, lane, c.mask, m.timestep);
       if (delta < c.tol) { c.result = 1; c.reached = 1; }
       if (c.steps > c.maxsteps) { c.result = 2; c.active = 0; continue; }
-      sim_step(ws, wi, lane, &status, true);
+      sim_step(ws, wi, lane, &status, stage_sync != 0);
       stepped = true;
       c.steps++; nstep++;
       if (c.reached) c.active = 0;
       break;
     }
-    if (!stepped) stage_barriers_idle();
+    if (!stepped) stage_barriers_idle(stage_sync != 0);
   }
   if (!busy) return;
   // a movement that just ended inside the last iteration still has to hand over to the program (no sub-step involved)
@@ -249,6 +249,7 @@ struct ge_engine {
   double base_pos[3];
   int64_t launches, substep_launches;
   int wpb;           // warps (= envs) per CTA of the sub-step kernel
+  int stage_sync;    // CTA barriers between the stages of a sub-step (instruction-cache sharing)
   int* d_nout; double* d_dbg;
   RenderCtx rctx;
 };
@@ -287,7 +288,7 @@ static void make_layout(const DevModel& m, Layout& L) {
   // phase A (kinematics/dynamics/collision)
   int a = L.scratch;
   auto takeA = [&](int n) { int r = a; a += align_up(n, 2); return r; };
-  L.gpos = takeA(3 * ng); L.gmat = takeA(9 * ng);          // alive until the end of collision
+  L.gpos = takeA(3 * ng); L.gmat = takeA(9 * ng); L.gcen = takeA(3 * ng);  // alive until the end of collision
   L.cinert = takeA(10 * nb);                               // alive until CRB
   L.xpos = takeA(3 * nb); L.xquat = takeA(4 * nb); L.xmat = takeA(9 * nb); L.xipos = takeA(3 * nb);
   int a_fk = a;
@@ -353,7 +354,7 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
   m.geom_obbcenter = PD("geom_obbcenter"); m.geom_obbhalf = PD("geom_obbhalf"); m.geom_rgba = PD("geom_rgba");
   m.mesh_vertadr = PI("mesh_vertadr"); m.mesh_vertnum = PI("mesh_vertnum"); m.mesh_faceadr = PI("mesh_faceadr"); m.mesh_facenum = PI("mesh_facenum");
   m.mesh_vert = PD("mesh_vert"); m.mesh_center = PD("mesh_center"); m.mesh_faceplane = PD("mesh_faceplane");
-  m.pair_geom = PI("pair_geom"); m.pair_condim = PI("pair_condim"); m.pair_friction = PD("pair_friction"); m.pair_margin = PD("pair_margin");
+  m.pair_geom = PI("pair_geom"); m.pair_rec = PI("pair_rec"); m.pair_rsum = PD("pair_rsum"); m.pair_condim = PI("pair_condim"); m.pair_friction = PD("pair_friction"); m.pair_margin = PD("pair_margin");
   m.pair_solref = PD("pair_solref"); m.pair_solimp = PD("pair_solimp");
   m.actuator_jntid = PI("actuator_jntid"); m.actuator_gear = PD("actuator_gear"); m.actuator_ctrlrange = PD("actuator_ctrlrange");
   m.eq_jnt1 = PI("eq_jnt1"); m.eq_jnt2 = PI("eq_jnt2"); m.eq_polycoef = PD("eq_polycoef"); m.eq_solref = PD("eq_solref"); m.eq_solimp = PD("eq_solimp");
@@ -380,6 +381,8 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
   // warps (= envs) per CTA; measured on B200 with stage barriers: 2/3/4/7 -> 1.46/1.51/1.10/1.35 M sub-steps/s; GE_WPB overrides
   h->wpb = 3;
   if (h->wpb * h->lay.total_bytes > 227 * 1024) h->wpb = 1;
+  h->stage_sync = 1;
+  if (const char* ev = getenv("GE_STAGE_SYNC")) h->stage_sync = atoi(ev) != 0;
   if (const char* ev = getenv("GE_WPB")) { int v = atoi(ev); if (v >= 1 && v <= 8 && v * h->lay.total_bytes <= 227 * 1024) h->wpb = v; }
   if (h->wpb < 1) { cudaFree(h->dblob); delete h; return fail(GE_ERR_MODEL, "model too large for the per-warp shared-memory workspace"); }
   CK(cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, h->wpb * h->lay.total_bytes));
@@ -507,7 +510,7 @@ extern "C" int ge_run_async(ge_handle h, int substeps) {
   if (bind(h)) return GE_ERR_CUDA;
   dim3 blk(32, h->wpb);
   k_run<<<(h->n_envs + h->wpb - 1) / h->wpb, blk, (size_t)h->wpb * h->lay.total_bytes, h->stream>>>(h->E, h->n_envs, substeps, h->base_pos[0], h->base_pos[1],
-                                                                                                   h->base_pos[2]);
+                                                                                                   h->base_pos[2], h->stage_sync);
   h->launches++; h->substep_launches++;
   CK(cudaGetLastError());
   return GE_OK;

@@ -361,6 +361,13 @@ def compile_mjcf(path):
         pair_solref[i] = 0.5 * (a["solref"] + b["solref"])
         pair_solimp[i] = 0.5 * (a["solimp"] + b["solimp"])
 
+    # compact broad-phase records: (geom1, geom2, type1, type2) and the bounding-sphere reach of the pair
+    pair_rec = np.zeros((npair, 4), np.int32)
+    pair_rsum = np.zeros(npair)
+    for i, (g1, g2) in enumerate(pairs):
+        pair_rec[i] = [g1, g2, geoms[g1]["type"], geoms[g2]["type"]]
+        pair_rsum[i] = (0.0 if geoms[g1]["type"] == G_PLANE else geom_rbound[g1]) + geom_rbound[g2] + pair_margin[i]
+
     # ---- actuators, equality
     act = root.find("actuator")
     jname = {j["name"]: i for i, j in enumerate(joints)}
@@ -427,7 +434,7 @@ def compile_mjcf(path):
         mesh_vert=np.concatenate(mesh_vert) if mesh_vert else np.zeros((0, 3)),
         mesh_face=np.concatenate(mesh_face).astype(np.int32) if mesh_face else np.zeros((0, 3), np.int32),
         mesh_center=np.array(mesh_center).reshape(len(meshes), 3),
-        pair_geom=pair_geom, pair_condim=pair_condim, pair_friction=pair_friction, pair_margin=pair_margin,
+        pair_geom=pair_geom, pair_condim=pair_condim, pair_rec=pair_rec, pair_rsum=pair_rsum, pair_friction=pair_friction, pair_margin=pair_margin,
         pair_solref=pair_solref, pair_solimp=pair_solimp,
         actuator_jntid=np.array([m["jnt"] for m in motors], np.int32),
         actuator_gear=np.array([m["gear"] for m in motors]),
