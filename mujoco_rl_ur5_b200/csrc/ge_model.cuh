@@ -6,8 +6,8 @@
 
 #define GE_NU 7          // actuators of the UR5 + 2-finger gripper scenes (MujocoController.py:157-235)
 #define GE_MAXCON 32     // contacts kept per environment (overflow is flagged in the status word)
-#define GE_MAXCAND 96    // narrow-phase candidate pairs per environment
-#define GE_MAXSR 24      // "simple" constraint rows: joint equality + joint limits (<= 2 non-zeros each)
+#define GE_MAXCAND 64    // narrow-phase candidate pairs per environment
+#define GE_MAXSR 16      // "simple" constraint rows: joint equality + joint limits (<= 2 non-zeros each)
 #define GE_MAXCHAIN 24   // longest dof list of one contact (both kinematic chains)
 
 enum { G_PLANE = 0, G_SPHERE = 2, G_CAPSULE = 3, G_CYLINDER = 5, G_BOX = 6, G_MESH = 7 };

@@ -58,7 +58,7 @@ __device__ __noinline__ void stage_fk(double* ws, int lane) {
     for (int c = 0; c < 4; c++) lquat[4 * b + c] = quat[c];
   }
   __syncwarp();
-  double *xpos = ws + L.xpos, *xquat = ws + L.xquat, *xmat = ws + L.xmat, *xipos = ws + L.xipos;
+  double *xpos = ws + L.xpos, *xmat = ws + L.xmat;
   LANE_LOOP(b, m.nbody) {
     double pos[3], quat[4], t[3], nq[4];
     v3copy(pos, lpos + 3 * b);
@@ -70,11 +70,9 @@ __device__ __noinline__ void stage_fk(double* ws, int lane) {
     }
     qnormalize(quat);
     v3copy(xpos + 3 * b, pos);
-    for (int c = 0; c < 4; c++) xquat[4 * b + c] = quat[c];
     double R[9];
     q2mat(R, quat);
     for (int c = 0; c < 9; c++) xmat[9 * b + c] = R[c];
-    m3mulv(t, R, m.body_ipos + 3 * b); v3add(xipos + 3 * b, pos, t);
   }
   __syncwarp();
   double* cdof = ws + L.cdof;
@@ -92,11 +90,13 @@ __device__ __noinline__ void stage_fk(double* ws, int lane) {
     if (type == J_SLIDE) { v3set(c, 0, 0, 0); v3copy(c + 3, ax); }
     else { v3copy(c, ax); v3cross(c + 3, an, ax); }
   }
+  __syncwarp();  // the local joint frames (janchor, jaxis) are dead from here on: cinert overwrites them
   double* cinert = ws + L.cinert;
   LANE_LOOP(b, m.nbody) {
     double* I = cinert + 10 * b;
     double mass = m.body_mass[b];
-    const double* c = xipos + 3 * b;
+    double c[3];
+    m3mulv(c, xmat + 9 * b, m.body_ipos + 3 * b); v3add(c, c, xpos + 3 * b);
     const double* R = xmat + 9 * b;
     const double* Ib = m.body_inertia + 6 * b;
     double Il[9] = {Ib[0], Ib[3], Ib[4], Ib[3], Ib[1], Ib[5], Ib[4], Ib[5], Ib[2]}, RI[9], Rt[9], Iw[9];

@@ -245,7 +245,12 @@ __device__ __noinline__ double rows_cost(double* ws, const int* wi, int ncon, in
 namespace ge {
 
 // Newton solver; returns the number of iterations. Output: ws[qacc], ws[qfrc_constraint].
-__device__ __noinline__ int solve_newton(double* ws, int* wi, int lane, int ncon, int nsr) {
+// CTA barriers inside the FIRST Newton iteration (which every stepping warp executes): keeps the warps of a CTA on the same
+// code so that they share instruction-cache lines; later iterations run unsynchronised.
+#define GE_NEWTON_BARRIERS 4
+__device__ __forceinline__ void newton_barrier(bool sync) { if (sync) __syncthreads(); }
+
+__device__ __noinline__ int solve_newton(double* ws, int* wi, int lane, int ncon, int nsr, bool sync = false) {
   const DevModel& m = c_m; const Layout& L = c_L;
   int nv = m.nv;
   double *qacc = ws + L.qacc, *qacc_smooth = ws + L.qacc_smooth, *qfrc_smooth = ws + L.qfrc_smooth, *qaccws = ws + L.qaccws;
@@ -254,7 +259,7 @@ __device__ __noinline__ int solve_newton(double* ws, int* wi, int lane, int ncon
   const int ja = c_ja(), jv = c_jv();
   LANE_LOOP(d, nv) { qacc[d] = qacc_smooth[d]; qfc[d] = 0; }
   __syncwarp();
-  if (ncon + nsr == 0) return 0;
+  if (ncon + nsr == 0) { for (int k = 0; k < GE_NEWTON_BARRIERS; k++) newton_barrier(sync); return 0; }
   // warm start choice
   LANE_LOOP(d, nv) grad[d] = qaccws[d] - qacc_smooth[d];
   __syncwarp();
@@ -285,7 +290,9 @@ __device__ __noinline__ int solve_newton(double* ws, int* wi, int lane, int ncon
     gn = warp_sum(gn);
     __syncwarp();
     if (it > 0 && scale * sqrt(gn) < m.tolerance) break;
+    if (it == 0) newton_barrier(sync);
     build_hessian(ws, wi, ncon, nsr, lane);
+    if (it == 0) newton_barrier(sync);
     cholesky_solve(ws, wi, search, grad, lane);
     mul_M(qM, Mv, search, lane);
     double g1 = 0, g2 = 0, sn = 0;
@@ -293,6 +300,7 @@ __device__ __noinline__ int solve_newton(double* ws, int* wi, int lane, int ncon
     g1 = warp_sum(g1); g2 = warp_sum(g2); sn = sqrt(warp_sum(sn));
     body_vel(ws, search, lane); contact_base(ws, wi, ncon, jv, lane); simple_base(ws, wi, nsr, search, SR_JV, lane);
     __syncwarp();
+    if (it == 0) newton_barrier(sync);
     // exact line search: safeguarded 1-D Newton on the convex piecewise-quadratic cost along `search`
     double gtol = m.tolerance * 0.01 * sn * m.meaninertia * (nv > 1 ? nv : 1);
     if (gtol < GE_MINVAL) gtol = GE_MINVAL;
@@ -321,6 +329,7 @@ __device__ __noinline__ int solve_newton(double* ws, int* wi, int lane, int ncon
       if (hi >= 0 && (next <= lo || next >= hi)) next = 0.5 * (lo + hi);
       alpha = next;
     }
+    if (it == 0) newton_barrier(sync);
     niter = it + 1;
     if (alpha == 0) break;
     LANE_LOOP(d, nv) { qacc[d] += alpha * search[d]; Ma[d] += alpha * Mv[d]; }

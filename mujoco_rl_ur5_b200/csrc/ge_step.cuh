@@ -20,7 +20,7 @@ struct StepInfo { int ncon, nsr, niter; };
 #ifndef GE_STAGE_SYNC
 #define GE_STAGE_SYNC 1
 #endif
-#define GE_NUM_STAGE_BARRIERS 3
+#define GE_NUM_STAGE_BARRIERS (3 + GE_NEWTON_BARRIERS)
 __device__ __forceinline__ void stage_barrier(bool sync) { if (GE_STAGE_SYNC && sync) __syncthreads(); }
 __device__ __forceinline__ void stage_barriers_idle(bool on) { if (GE_STAGE_SYNC && on) for (int k = 0; k < GE_NUM_STAGE_BARRIERS; k++) __syncthreads(); }
 
@@ -29,10 +29,10 @@ __device__ __noinline__ StepInfo forward(double* ws, int* wi, int lane, int* sta
   const DevModel& m = c_m; const Layout& L = c_L;
   StepInfo si;
   stage_fk(ws, lane);
+  stage_barrier(sync);
+  si.ncon = stage_collision(ws, wi, lane, status);  // needs the geom frames only; bias forces / mass matrix reuse their storage
   stage_rne(ws, lane);  // qfrc_smooth := bias
   stage_crb(ws, lane);
-  stage_barrier(sync);
-  si.ncon = stage_collision(ws, wi, lane, status);
   // smooth forces: passive (joint damping) - bias + actuation (torque motors, gear * clamp(ctrl))
   const double *qvel = ws + L.qvel, *ctrl = ws + L.ctl + CTL_CTRL;
   double *qfs = ws + L.qfrc_smooth, *qas = ws + L.qacc_smooth;
@@ -56,7 +56,7 @@ __device__ __noinline__ StepInfo forward(double* ws, int* wi, int lane, int* sta
   }
   stage_barrier(sync);
   si.nsr = stage_constraints(ws, wi, lane, si.ncon, status);
-  si.niter = solve_newton(ws, wi, lane, si.ncon, si.nsr);
+  si.niter = solve_newton(ws, wi, lane, si.ncon, si.nsr, GE_STAGE_SYNC && sync);
   if (si.niter >= m.iterations) *status |= 4;
   LANE_LOOP(d, m.nv) ws[L.qaccws + d] = ws[L.qacc + d];
   __syncwarp();

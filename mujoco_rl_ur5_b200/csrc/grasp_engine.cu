@@ -273,12 +273,17 @@ static int64_t blob_off(const std::vector<char>& b, const char* name) {
 
 static int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
-static void make_layout(const DevModel& m, Layout& L) {
+static void make_layout(const DevModel& m, Layout& L, const int* tree_dofnum_h, const int* tree_simple_h, int ntree_dofnum_n) {
   int nb = m.nbody, nj = m.njnt, nv = m.nv, ng = m.ngeom;
   int o = 0;
   auto take = [&](int n) { int r = o; o += align_up(n, 2); return r; };
   L.qpos = take(m.nq); L.qvel = take(nv); L.qaccws = take(nv); L.ctl = take(32);
-  L.cdof = take(6 * nv); L.qM = take(m.nM); L.qLD = take(m.nM);
+  L.cdof = take(6 * nv); L.qM = take(m.nM);
+  {  // the tree-sparse L^T D L factor is only needed when a tree is too wide for the lane-group mass solve
+    bool need = false;
+    for (int t = 0; t < ntree_dofnum_n; t++) if (tree_dofnum_h[t] > 8 && !tree_simple_h[t]) need = true;
+    L.qLD = need ? take(m.nM) : L.qM;
+  }
   L.qfrc_smooth = take(nv); L.qacc_smooth = take(nv); L.qfrc_constraint = take(nv); L.qacc = take(nv);
   L.Ma = take(nv); L.grad = take(nv); L.search = take(nv); L.Mv = take(nv);
   L.cstride = align_up(C_MU + 4 * m.maxdim - 1, 2);
@@ -286,19 +291,27 @@ static void make_layout(const DevModel& m, Layout& L) {
   L.sr = take(6 * GE_MAXSR);
   L.scratch = o;
   // phase A (kinematics/dynamics/collision)
+  // phase A (kinematics -> collision -> bias forces / mass matrix); order of use:
+  //   stage_fk writes everything; stage_collision needs gpos/gmat/gcen only; stage_rne + stage_crb need cinert (+ their own
+  //   temporaries, which overwrite the geom frames and body poses that are dead by then)
   int a = L.scratch;
   auto takeA = [&](int n) { int r = a; a += align_up(n, 2); return r; };
   L.gpos = takeA(3 * ng); L.gmat = takeA(9 * ng); L.gcen = takeA(3 * ng);  // alive until the end of collision
-  L.cinert = takeA(10 * nb);                               // alive until CRB
-  L.xpos = takeA(3 * nb); L.xquat = takeA(4 * nb); L.xmat = takeA(9 * nb); L.xipos = takeA(3 * nb);
-  int a_fk = a;
-  L.lpos = takeA(3 * nb); L.lquat = takeA(4 * nb); L.janchor = takeA(3 * nj); L.jaxis = takeA(3 * nj);
+  L.xpos = takeA(3 * nb); L.xmat = takeA(9 * nb);                            // alive until the end of stage_fk
+  L.xquat = L.xpos; L.xipos = L.xpos;                                        // (not stored any more)
+  int a_local = a;
+  L.lpos = takeA(3 * nb); L.lquat = takeA(4 * nb); L.janchor = takeA(3 * nj); L.jaxis = takeA(3 * nj);  // dead before cinert is written
   int endA1 = a;
-  // RNE temporaries reuse everything after cinert except nothing needed: xpos.. are dead once cdof/cinert/gpos exist
-  a = L.xpos;
+  L.cinert = a_local;                                                         // alive until CRB
+  if (a_local + 10 * nb > endA1) endA1 = a_local + align_up(10 * nb, 2);
+  // RNE / CRB temporaries start at the scratch base (geom frames and body poses are dead after collision) and must end below cinert
+  a = L.scratch;
   L.cdofdot = takeA(6 * nv); L.cvel = takeA(6 * nb); L.cacc = takeA(6 * nb); L.cfrc = takeA(6 * nb);
   int endA2 = a;
-  (void)a_fk;
+  if (endA2 > L.cinert) {  // not enough room below cinert: move cinert (and the local frames) up
+    int shift = endA2 - L.cinert;
+    L.cinert += shift; L.lpos += shift; L.lquat += shift; L.janchor += shift; L.jaxis += shift; endA1 += shift;
+  }
   // phase B (solver)
   int b = L.scratch;
   auto takeB = [&](int n) { int r = b; b += align_up(n, 2); return r; };
@@ -375,12 +388,22 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
     if (!bp) { cudaFree(h->dblob); delete h; return fail(GE_ERR_MODEL, "blob entry missing: %s", "ik_base_pos"); }
     memcpy(h->base_pos, bp, 24);
   }
-  make_layout(m, h->lay);
+  make_layout(m, h->lay, (const int*)blob_find(B, "tree_dofnum", nullptr), (const int*)blob_find(B, "tree_simple", nullptr), m.ntree);
   CK(cudaMemcpyToSymbol(c_m, &m, sizeof m));
   CK(cudaMemcpyToSymbol(c_L, &h->lay, sizeof(Layout)));
-  // warps (= envs) per CTA; measured on B200 with stage barriers: 2/3/4/7 -> 1.46/1.51/1.10/1.35 M sub-steps/s; GE_WPB overrides
-  h->wpb = 3;
-  if (h->wpb * h->lay.total_bytes > 227 * 1024) h->wpb = 1;
+  // warps (= envs) per CTA: maximise the resident warps per SM (228 KB shared memory per SM, 1 KB reserved per CTA, 227 KB max per
+  // CTA); ties go to the smaller CTA (less barrier imbalance).  r01 sweeps are in DESIGN.md; GE_WPB overrides.
+  {
+    int best = 1, best_warps = 0;
+    for (int w = 1; w <= 8; w++) {
+      long per_cta = (long)w * h->lay.total_bytes;
+      if (per_cta > 227 * 1024) break;
+      int ctas = (int)(233472 / (per_cta + 1024));
+      if (ctas > 32) ctas = 32;
+      if (w * ctas > best_warps) { best_warps = w * ctas; best = w; }
+    }
+    h->wpb = best;
+  }
   h->stage_sync = 1;
   if (const char* ev = getenv("GE_STAGE_SYNC")) h->stage_sync = atoi(ev) != 0;
   if (const char* ev = getenv("GE_WPB")) { int v = atoi(ev); if (v >= 1 && v <= 8 && v * h->lay.total_bytes <= 227 * 1024) h->wpb = v; }
@@ -436,7 +459,7 @@ extern "C" int ge_size(ge_handle h, int what) {
   if (!h) return GE_ERR_ARG;
   switch (what) {
     case 0: return h->hm.nq; case 1: return h->hm.nv; case 2: return h->hm.nbody; case 3: return h->hm.ngeom; case 4: return h->hm.nu;
-    case 5: return h->n_envs; case 6: return GE_MAXCON; case 7: return h->lay.total_bytes;
+    case 5: return h->n_envs; case 6: return GE_MAXCON; case 7: return h->lay.total_bytes; case 8: return h->wpb;
   }
   return GE_ERR_ARG;
 }
