@@ -351,9 +351,8 @@ __device__ __noinline__ void col_sphere_box(const double* ws, int g1, int g2, do
   out.dist[0] = dist; out.n = 1;
 }
 
-__device__ __noinline__ int clip_poly(const double (*p)[2], int n, int axis, double lim, double (*out)[2]) {
+__device__ __forceinline__ int clip_poly(const double (*p)[2], int n, int axis, double lim, double (*out)[2]) {
   int k = 0;
-  #pragma unroll 1
   for (int i = 0; i < n; i++) {
     const double *a = p[i], *b = p[(i + 1 == n) ? 0 : i + 1];
     double da = a[axis] - lim, db = b[axis] - lim;
@@ -369,25 +368,20 @@ __device__ __noinline__ void col_box_box(const double* ws, int g1, int g2, doubl
   const double *h1 = m.geom_size + 3 * g1, *h2 = m.geom_size + 3 * g2;
   double d[3], a[3][3], b[3][3], C[3][3], AC[3][3];
   v3sub(d, c2, c1);
-  #pragma unroll 1
   for (int i = 0; i < 3; i++) { m3col(a[i], R1, i); m3col(b[i], R2, i); }
-  #pragma unroll 1
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { C[i][j] = v3dot(a[i], b[j]); AC[i][j] = fabs(C[i][j]); }
   double best_s = -1e300; int best_axis = -1;
-  #pragma unroll 1
   for (int i = 0; i < 3; i++) {
     double s = fabs(v3dot(d, a[i])) - (h1[i] + h2[0] * AC[i][0] + h2[1] * AC[i][1] + h2[2] * AC[i][2]);
     if (s >= margin) return;
     if (s > best_s) { best_s = s; best_axis = i; }
   }
-  #pragma unroll 1
   for (int j = 0; j < 3; j++) {
     double s = fabs(v3dot(d, b[j])) - (h2[j] + h1[0] * AC[0][j] + h1[1] * AC[1][j] + h1[2] * AC[2][j]);
     if (s >= margin) return;
     if (s > best_s) { best_s = s; best_axis = 3 + j; }
   }
   double edge_s = -1e300; int ei = -1, ej = -1; double en[3] = {0, 0, 0};
-  #pragma unroll 1
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
     double Lx[3];
     v3cross(Lx, a[i], b[j]);
@@ -395,7 +389,6 @@ __device__ __noinline__ void col_box_box(const double* ws, int g1, int g2, doubl
     if (len < 1e-6) continue;
     v3scl(Lx, Lx, 1.0 / len);
     double ra = 0, rb = 0;
-    #pragma unroll 1
     for (int k = 0; k < 3; k++) { ra += h1[k] * fabs(v3dot(Lx, a[k])); rb += h2[k] * fabs(v3dot(Lx, b[k])); }
     double s = fabs(v3dot(d, Lx)) - ra - rb;
     if (s >= margin) return;
@@ -406,7 +399,6 @@ __device__ __noinline__ void col_box_box(const double* ws, int g1, int g2, doubl
     v3copy(n, en);
     if (v3dot(d, n) < 0) v3scl(n, n, -1.0);
     v3copy(p1, c1); v3copy(p2, c2);
-    #pragma unroll 1
     for (int k = 0; k < 3; k++) {
       if (k != ei) v3addscl(p1, p1, a[k], (v3dot(n, a[k]) >= 0 ? 1.0 : -1.0) * h1[k]);
       if (k != ej) v3addscl(p2, p2, b[k], (v3dot(n, b[k]) >= 0 ? -1.0 : 1.0) * h2[k]);
@@ -433,7 +425,6 @@ __device__ __noinline__ void col_box_box(const double* ws, int g1, int g2, doubl
   v3sub(dr, ci, cr);
   v3scl(nref, ar[ax], v3dot(dr, ar[ax]) >= 0 ? 1.0 : -1.0);
   int inc = 0; double bestd = -1;
-  #pragma unroll 1
   for (int k = 0; k < 3; k++) { double s = fabs(v3dot(ai[k], nref)); if (s > bestd) { bestd = s; inc = k; } }
   double sgn = v3dot(ai[inc], nref) > 0 ? -1.0 : 1.0;
   double fc[3];
@@ -441,7 +432,6 @@ __device__ __noinline__ void col_box_box(const double* ws, int g1, int g2, doubl
   int u1 = (inc + 1) % 3, u2 = (inc + 2) % 3, r1 = (ax + 1) % 3, r2 = (ax + 2) % 3;
   double poly[16][2], tmp[16][2], height[4];
   const double sg[4][2] = {{1, 1}, {-1, 1}, {-1, -1}, {1, -1}};
-  #pragma unroll 1
   for (int k = 0; k < 4; k++) {
     double corner[3], rel[3];
     v3addscl(corner, fc, ai[u1], sg[k][0] * hi[u1]); v3addscl(corner, corner, ai[u2], sg[k][1] * hi[u2]);
@@ -458,19 +448,14 @@ __device__ __noinline__ void col_box_box(const double* ws, int g1, int g2, doubl
   double g0 = height[0] - gx * poly[0][0] - gy * poly[0][1];
   int n = 4;
   n = clip_poly(poly, n, 0, hr[r1], tmp); if (!n) return;
-  #pragma unroll 1
   for (int k = 0; k < n; k++) tmp[k][0] = -tmp[k][0];
   n = clip_poly(tmp, n, 0, hr[r1], poly); if (!n) return;
-  #pragma unroll 1
   for (int k = 0; k < n; k++) poly[k][0] = -poly[k][0];
   n = clip_poly(poly, n, 1, hr[r2], tmp); if (!n) return;
-  #pragma unroll 1
   for (int k = 0; k < n; k++) tmp[k][1] = -tmp[k][1];
   n = clip_poly(tmp, n, 1, hr[r2], poly); if (!n) return;
-  #pragma unroll 1
   for (int k = 0; k < n; k++) poly[k][1] = -poly[k][1];
   v3scl(out.normal, nref, ref1 ? 1.0 : -1.0);
-  #pragma unroll 1
   for (int k = 0; k < n && out.n < 8; k++) {
     double dist = g0 + gx * poly[k][0] + gy * poly[k][1];
     if (dist >= margin) continue;
