@@ -18,8 +18,10 @@ const char* gq_version(void);
 
 /* nn.Conv2d(Cin, Cout, kernel_size=ks, padding=ks/2, stride=1) for ks in {1,3}, Cin and Cout multiples of 64 (conv3x3: Modules.py:145-156;
  * BasicBlock.conv3 1x1 with bias: :126).  tcgen05 implicit GEMM.  x [B,H,W,Cin] bf16, w [Cout][ks*ks][Cin] bf16, bias [Cout] f32 or NULL,
- * y [B,H,W,Cout] f32.  If stats != NULL, stats[B][Cout][2] f32 += per-image (sum, sum of squares) of y over H*W (zero it first). */
-int gq_conv_tc(const void* x, const void* w, const float* bias, float* y, float* stats, int B, int H, int W, int Cin, int Cout, int ks, void* stream);
+ * y [B,H,W,Cout] f32.  If stats != NULL, stats[B][Cout][2] f32 := per-image (sum, sum of squares) of y over H*W, computed
+ * deterministically through `partials`, a scratch buffer of B * ceil(H*W/128) * 4 * Cout * 2 floats. */
+int gq_conv_tc(const void* x, const void* w, const float* bias, float* y, float* stats, float* partials, int B, int H, int W, int Cin, int Cout, int ks,
+               void* stream);
 /* Perception_Module.C1 = conv3x3(4, 64), no bias (Modules.py:163): x [B,4,H,W] f32 NCHW, w [64][3][3][4] f32, y [B,H,W,64] bf16 */
 int gq_conv_first(const float* x, const float* w, void* y, int B, int H, int W, void* stream);
 /* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) (Modules.py:164,166): x [B,H,W,C] -> y [B,ceil(H/2),ceil(W/2),C] */

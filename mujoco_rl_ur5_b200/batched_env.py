@@ -77,8 +77,11 @@ class BatchedGraspEnv:
         eng = self.engine
         if self.current_observation is None or self.step_called == 1:
             self.current_observation = self.get_observation()  # GraspingEnv.py:87-88
-        self._pin_action.copy_(t.as_tensor(np.asarray(action, dtype=np.int32).reshape(self.n_envs, 2)))
-        act = self._pin_action.to(eng.device, non_blocking=True)
+        if isinstance(action, t.Tensor) and action.is_cuda:  # actions already on the device (e.g. from BatchedGreedyAgent)
+            act = action.to(t.int32).reshape(self.n_envs, 2)
+        else:
+            self._pin_action.copy_(t.as_tensor(np.asarray(action, dtype=np.int32).reshape(self.n_envs, 2)))
+            act = self._pin_action.to(eng.device, non_blocking=True)
         W = self.IMAGE_WIDTH
         x = act[:, 0] % W
         y = t.div(act[:, 0], W, rounding_mode="floor")

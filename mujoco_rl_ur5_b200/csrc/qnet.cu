@@ -168,13 +168,25 @@ __global__ void __launch_bounds__(128) k_conv_tc(const bf16* __restrict__ x, con
         float s1 = mvalid ? v[i] : 0.f, s2 = s1 * s1;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-        if (lane == 0) { atomicAdd(stats + ((size_t)b * Cout + n0 + cb + i) * 2, s1); atomicAdd(stats + ((size_t)b * Cout + n0 + cb + i) * 2 + 1, s2); }
+        // deterministic: every (CTA, warp) writes its own partial, k_bn_reduce adds them in a fixed order
+        if (lane == 0) { float* pp = stats + ((((size_t)b * gridDim.x + blockIdx.x) * 4 + warp) * Cout + n0 + cb + i) * 2; pp[0] = s1; pp[1] = s2; }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tacc, BLOCK_N);
+}
+
+// per-image batch-norm statistics from the per-(tile, warp) partials of k_conv_tc, summed in a fixed order (double accumulation)
+__global__ void k_bn_reduce(const float* __restrict__ part, float* __restrict__ stats, int B, int nparts, int C) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  int b = i / C, c = i % C;
+  double s1 = 0, s2 = 0;
+  const float* p = part + ((size_t)b * nparts * C + c) * 2;
+  for (int k = 0; k < nparts; k++) { s1 += p[(size_t)k * C * 2]; s2 += p[(size_t)k * C * 2 + 1]; }
+  stats[(size_t)i * 2] = (float)s1; stats[(size_t)i * 2 + 1] = (float)s2;
 }
 
 // ------------------------------------------------------------------------------------------------ small layers
@@ -321,7 +333,8 @@ extern "C" int gq_obs_to_state(const unsigned char* rgb, const float* depth, flo
 }
 extern "C" const char* gq_version(void) { return "grasp_qnet 0.1 sm_100a bf16 tcgen05"; }
 
-extern "C" int gq_conv_tc(const void* x, const void* w, const float* bias, float* y, float* stats, int B, int H, int W, int Cin, int Cout, int ks, void* stream) {
+extern "C" int gq_conv_tc(const void* x, const void* w, const float* bias, float* y, float* stats, float* partials, int B, int H, int W, int Cin, int Cout, int ks,
+                          void* stream) {
   if (!x || !w || !y || (ks != 1 && ks != 3) || Cin % 64 || Cout % 64) { snprintf(q_err, sizeof q_err, "gq_conv_tc: bad argument"); return -1; }
   cudaStream_t st = (cudaStream_t)stream;
   int bn = (Cout % 128 == 0) ? 128 : 64;
@@ -329,10 +342,14 @@ extern "C" int gq_conv_tc(const void* x, const void* w, const float* bias, float
   size_t smem = 2 * (BM * BK * 2) + 2 * ((size_t)bn * BK * 2) + 64;
   if (bn == 128) {
     QCK(cudaFuncSetAttribute(k_conv_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_conv_tc<128><<<grid, 128, smem, st>>>((const bf16*)x, (const bf16*)w, bias, y, stats, H, W, Cin, Cout, ks);
+    k_conv_tc<128><<<grid, 128, smem, st>>>((const bf16*)x, (const bf16*)w, bias, y, stats ? partials : nullptr, H, W, Cin, Cout, ks);
   } else {
     QCK(cudaFuncSetAttribute(k_conv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_conv_tc<64><<<grid, 128, smem, st>>>((const bf16*)x, (const bf16*)w, bias, y, stats, H, W, Cin, Cout, ks);
+    k_conv_tc<64><<<grid, 128, smem, st>>>((const bf16*)x, (const bf16*)w, bias, y, stats ? partials : nullptr, H, W, Cin, Cout, ks);
+  }
+  if (stats) {
+    if (!partials) { snprintf(q_err, sizeof q_err, "gq_conv_tc: stats requested without a partials buffer"); return -1; }
+    k_bn_reduce<<<(B * Cout + 127) / 128, 128, 0, st>>>(partials, stats, B, (int)grid.x * 4, Cout);
   }
   QCK(cudaGetLastError());
   return 0;

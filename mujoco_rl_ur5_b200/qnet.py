@@ -32,7 +32,7 @@ def load_qnet_library():
         P, I, F = C.c_void_p, C.c_int, C.c_float
         L.gq_last_error.restype = C.c_char_p
         L.gq_version.restype = C.c_char_p
-        L.gq_conv_tc.argtypes = [P, P, P, P, P, I, I, I, I, I, I, P]
+        L.gq_conv_tc.argtypes = [P, P, P, P, P, P, I, I, I, I, I, I, P]
         L.gq_conv_first.argtypes = [P, P, P, I, I, I, P]
         L.gq_maxpool.argtypes = [P, P, I, I, I, I, P]
         L.gq_bn_act.argtypes = [P, P, P, P, P, P, I, I, I, F, P]
@@ -145,8 +145,9 @@ class QNetForward:
     def conv_tc(self, x, w, bias, B, H, W, cin, cout, ks, want_stats):
         t = self.torch
         y = t.empty((B, H, W, cout), dtype=t.float32, device=self.dev)
-        stats = t.zeros((B, cout, 2), dtype=t.float32, device=self.dev) if want_stats else None
-        self._ck(self.L.gq_conv_tc(self._p(x), self._p(w), self._p(bias), self._p(y), self._p(stats), B, H, W, cin, cout, ks, self._stream()), "gq_conv_tc")
+        stats = t.empty((B, cout, 2), dtype=t.float32, device=self.dev) if want_stats else None
+        part = t.empty((B, (H * W + 127) // 128 * 4, cout, 2), dtype=t.float32, device=self.dev) if want_stats else None
+        self._ck(self.L.gq_conv_tc(self._p(x), self._p(w), self._p(bias), self._p(y), self._p(stats), self._p(part), B, H, W, cin, cout, ks, self._stream()), "gq_conv_tc")
         return y, stats
 
     def bn_act(self, x, stats, gamma, beta, identity, B, HW, Cc):
