@@ -39,7 +39,8 @@ int ge_create(const void* model_blob /*[host]*/, size_t nbytes, int n_envs, int 
 int ge_destroy(ge_handle h);
 
 /* model sizes: what = 0 nq, 1 nv, 2 nbody, 3 ngeom, 4 nu, 5 n_envs, 6 max contacts per env, 7 shared-memory bytes per env,
- * 8 environments (warps) per CTA of the sub-step kernel */
+ * 8 environments (warps) per CTA of the sub-step kernel, 9 workspace placement (0 shared memory, 1 HBM rows: scenes whose per-env
+ * workspace exceeds 227 KB, e.g. the 40-object scene) */
 int ge_size(ge_handle h, int what);
 
 /* MujocoEnv.set_state + controller re-sync, as GraspEnv.reset_model does (GraspingEnv.py:466-470):

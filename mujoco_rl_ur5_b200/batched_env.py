@@ -31,12 +31,40 @@ def scene_a_reset_qpos(arrays, seed):
     return q
 
 
+def random_unit_quaternion(r1, r2, r3):
+    """pyquaternion's Quaternion.random() from its three uniforms: (w, x, y, z)"""
+    s1, s2 = np.sqrt(1.0 - r1), np.sqrt(r1)
+    t1, t2 = 2 * np.pi * r2, 2 * np.pi * r3
+    return np.array([s1 * np.sin(t1), s1 * np.cos(t1), s2 * np.sin(t2), s2 * np.cos(t2)])
+
+
+def scene_b_reset_qpos(arrays, seed=None, rng=None):
+    """Scene-B reset, the live code of GraspingEnv.py:418-430: 40 free objects, per object x~U(-.25,.25), y~U(-.77,-.43),
+    z~U(1.0,1.5), orientation = Quaternion.random() (three more uniforms); draw order x, y, z, r1, r2, r3.  `rng`: a
+    RandomState, or numpy's global stream (what the reference uses) when both arguments are None."""
+    if rng is None:
+        rng = np.random.RandomState(seed) if seed is not None else np.random
+    q = np.array(arrays["qpos0"], dtype=np.float64).copy()
+    q[:7] = HOME
+    q[7] = HOME[6]
+    nobj = (len(q) - 8) // 7
+    for i in range(nobj):
+        a = 8 + 7 * i
+        q[a] = rng.uniform(low=-0.25, high=0.25)
+        q[a + 1] = rng.uniform(low=-0.77, high=-0.43)
+        q[a + 2] = rng.uniform(low=1.0, high=1.5)
+        r1, r2, r3 = rng.random_sample(3)
+        q[a + 3:a + 7] = random_unit_quaternion(r1, r2, r3)
+    return q
+
+
 class BatchedGraspEnv:
     def __init__(self, n_envs, scene="A", device=0, image_width=200, image_height=200, seed_base=20000, env_index_offset=0,
                  settle_ms=1000):
         import torch
 
         self.torch = torch
+        self.scene = scene
         self.blob = load_scene_blob(scene)
         self.arrays, self.names = load_scene(scene)
         self.engine = BatchedEngine(self.blob, n_envs, device)
@@ -59,7 +87,8 @@ class BatchedGraspEnv:
     def reset(self):
         """GraspEnv.reset_model (GraspingEnv.py:409-477): randomise objects, arm to HOME, settle, observe."""
         seeds = self.seed_base + self.env_index_offset + np.arange(self.n_envs) + 100003 * self.episode
-        q = np.stack([scene_a_reset_qpos(self.arrays, int(s)) for s in seeds])
+        rule = scene_b_reset_qpos if self.scene == "B" else scene_a_reset_qpos
+        q = np.stack([rule(self.arrays, int(s)) for s in seeds])
         self.episode += 1
         eng = self.engine
         eng.set_state(q)

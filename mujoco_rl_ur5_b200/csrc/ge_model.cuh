@@ -5,8 +5,8 @@
 #include <stdint.h>
 
 #define GE_NU 7          // actuators of the UR5 + 2-finger gripper scenes (MujocoController.py:157-235)
-#define GE_MAXCON 32     // contacts kept per environment (overflow is flagged in the status word)
-#define GE_MAXCAND 64    // narrow-phase candidate pairs per environment
+// contacts kept per environment / narrow-phase candidate pairs: Layout::maxcon, Layout::maxcand (chosen per scene at ge_create;
+// overflow is flagged in the status word)
 #define GE_MAXSR 16      // "simple" constraint rows: joint equality + joint limits (<= 2 non-zeros each)
 #define GE_MAXCHAIN 24   // longest dof list of one contact (both kinematic chains)
 
@@ -55,6 +55,9 @@ struct Layout {
   int i_cb1, i_cb2, i_ct1, i_ct2, i_cdim, i_cpair, i_cact, i_srA, i_srB, i_srtype, i_sract, i_cand, i_first, i_tcoupled, i_tcount, i_tlist, i_misc;
   int total_ints;
   int total_bytes;
+  int maxcon, maxcand;          // capacity of the contact / candidate lists
+  int fk_bytes;                 // bytes of the workspace prefix the kinematics stage touches (kinematics-only kernels)
+  int ws_global;                // 1: the per-env workspace lives in HBM (E.gws) because it does not fit shared memory
 };
 
 // per-environment state in HBM, row-major [N, ...]
@@ -71,4 +74,5 @@ struct EnvArrays {
   int* status;                    // [N]
   long long* substeps;            // [N]
   int* busy_count;                // [1]
+  double* gws;                    // [N, total_bytes/8] workspace rows when Layout::ws_global
 };

@@ -275,6 +275,115 @@ __device__ __forceinline__ void col_plane_sphere(const double* ws, int g1, int g
   v3addscl(out.pos[0], gpos + 3 * g2, n, -(r + 0.5 * dist));
   out.dist[0] = dist; out.n = 1;
 }
+// sphere vs capsule, capsule vs capsule, sphere vs cylinder: closed forms (mirror the oracle's functions of the same names)
+__device__ __noinline__ void col_sphere_capsule(const double* ws, int g1, int g2, double margin, PairContacts& out) {
+  const DevModel& m = c_m; const Layout& L = c_L;
+  const double *c = ws + L.gpos + 3 * g1, *p = ws + L.gpos + 3 * g2;
+  double ax[3], d[3], q[3], n[3];
+  m3col(ax, ws + L.gmat + 9 * g2, 2);
+  double r1 = m.geom_size[3 * g1], r2 = m.geom_size[3 * g2], h = m.geom_size[3 * g2 + 1];
+  v3sub(d, c, p);
+  double t = v3dot(d, ax);
+  if (t > h) t = h; else if (t < -h) t = -h;
+  v3addscl(q, p, ax, t); v3sub(d, q, c);
+  double len = v3norm(d);
+  if (len < 1e-12) { m3col(n, ws + L.gmat + 9 * g2, 0); len = 0; } else v3scl(n, d, 1.0 / len);
+  double dist = len - r1 - r2;
+  if (dist >= margin) return;
+  v3copy(out.normal, n);
+  v3addscl(out.pos[0], c, n, r1 + 0.5 * dist);
+  out.dist[0] = dist; out.n = 1;
+}
+__device__ __noinline__ void col_capsule_capsule(const double* ws, int g1, int g2, double margin, PairContacts& out) {
+  const DevModel& m = c_m; const Layout& L = c_L;
+  const double *p1 = ws + L.gpos + 3 * g1, *p2 = ws + L.gpos + 3 * g2;
+  double a1[3], a2[3], w[3], q1[3], q2[3], d[3], n[3];
+  m3col(a1, ws + L.gmat + 9 * g1, 2); m3col(a2, ws + L.gmat + 9 * g2, 2);
+  double r1 = m.geom_size[3 * g1], h1 = m.geom_size[3 * g1 + 1], r2 = m.geom_size[3 * g2], h2 = m.geom_size[3 * g2 + 1];
+  v3sub(w, p1, p2);
+  double b = v3dot(a1, a2), dd = v3dot(a1, w), ee = v3dot(a2, w), den = 1.0 - b * b, s, t;
+  if (den < 1e-10) {
+    double c2 = -dd, lo = c2 - h2, hi = c2 + h2;
+    if (lo < -h1) lo = -h1;
+    if (hi > h1) hi = h1;
+    s = lo <= hi ? 0.5 * (lo + hi) : (c2 > 0 ? h1 : -h1);
+  } else {
+    s = (b * ee - dd) / den;
+    if (s > h1) s = h1; else if (s < -h1) s = -h1;
+  }
+  t = b * s + ee;
+  if (t > h2) t = h2; else if (t < -h2) t = -h2;
+  s = b * t - dd;
+  if (s > h1) s = h1; else if (s < -h1) s = -h1;
+  v3addscl(q1, p1, a1, s); v3addscl(q2, p2, a2, t); v3sub(d, q2, q1);
+  double len = v3norm(d);
+  if (len < 1e-12) { v3cross(n, a1, a2); if (v3norm(n) < 1e-12) m3col(n, ws + L.gmat + 9 * g1, 0); v3normalize(n); len = 0; } else v3scl(n, d, 1.0 / len);
+  double dist = len - r1 - r2;
+  if (dist >= margin) return;
+  v3copy(out.normal, n);
+  v3addscl(out.pos[0], q1, n, r1 + 0.5 * dist);
+  out.dist[0] = dist; out.n = 1;
+}
+__device__ __noinline__ void col_sphere_cylinder(const double* ws, int g1, int g2, double margin, PairContacts& out) {
+  const DevModel& m = c_m; const Layout& L = c_L;
+  const double *c = ws + L.gpos + 3 * g1, *R = ws + L.gmat + 9 * g2;
+  double t[3], l[3], o[3], n[3];
+  v3sub(t, c, ws + L.gpos + 3 * g2); m3Tmulv(l, R, t);
+  double r1 = m.geom_size[3 * g1], r = m.geom_size[3 * g2], h = m.geom_size[3 * g2 + 1];
+  double rho = sqrt(l[0] * l[0] + l[1] * l[1]), sz = l[2] >= 0 ? 1.0 : -1.0, dz = fabs(l[2]) - h, dr = rho - r, sd;
+  double ux = rho > 1e-12 ? l[0] / rho : 1.0, uy = rho > 1e-12 ? l[1] / rho : 0.0;
+  if (dz <= 0 && dr <= 0) {
+    if (dr > dz) { v3set(o, ux, uy, 0); sd = dr; } else { v3set(o, 0, 0, sz); sd = dz; }
+  } else if (dz <= 0) { v3set(o, ux, uy, 0); sd = dr; }
+  else if (dr <= 0) { v3set(o, 0, 0, sz); sd = dz; }
+  else { sd = sqrt(dr * dr + dz * dz); v3set(o, dr * ux / sd, dr * uy / sd, sz * dz / sd); }
+  double dist = sd - r1;
+  if (dist >= margin) return;
+  m3mulv(n, R, o); v3scl(n, n, -1.0);
+  v3copy(out.normal, n);
+  v3addscl(out.pos[0], c, n, r1 + 0.5 * dist);
+  out.dist[0] = dist; out.n = 1;
+}
+// plane vs capsule: the two end spheres (+axis end first); plane vs cylinder: deepest rim point of each cap (+axis cap first),
+// a cap parallel to the plane contributes its centre (mirrors the oracle's col_plane_capsule / col_plane_cylinder)
+__device__ __noinline__ void col_plane_capsule(const double* ws, int g1, int g2, double margin, PairContacts& out) {
+  const DevModel& m = c_m; const Layout& L = c_L;
+  const double *gpos = ws + L.gpos, *gmat = ws + L.gmat;
+  double n[3], ax[3];
+  m3col(n, gmat + 9 * g1, 2); m3col(ax, gmat + 9 * g2, 2);
+  double r = m.geom_size[3 * g2], h = m.geom_size[3 * g2 + 1];
+  v3copy(out.normal, n);
+  for (int s = 0; s < 2; s++) {
+    double c[3], d[3];
+    v3addscl(c, gpos + 3 * g2, ax, s ? -h : h);
+    v3sub(d, c, gpos + 3 * g1);
+    double dist = v3dot(d, n) - r;
+    if (dist >= margin) continue;
+    v3addscl(out.pos[out.n], c, n, -(r + 0.5 * dist));
+    out.dist[out.n] = dist; out.n++;
+  }
+}
+__device__ __noinline__ void col_plane_cylinder(const double* ws, int g1, int g2, double margin, PairContacts& out) {
+  const DevModel& m = c_m; const Layout& L = c_L;
+  const double *gpos = ws + L.gpos, *gmat = ws + L.gmat;
+  double n[3], ax[3], rim[3];
+  m3col(n, gmat + 9 * g1, 2); m3col(ax, gmat + 9 * g2, 2);
+  double r = m.geom_size[3 * g2], h = m.geom_size[3 * g2 + 1];
+  v3addscl(rim, n, ax, -v3dot(n, ax));
+  double len = v3norm(rim);
+  if (len > 1e-6) v3scl(rim, rim, -r / len); else v3set(rim, 0, 0, 0);
+  v3copy(out.normal, n);
+  for (int s = 0; s < 2; s++) {
+    double c[3], d[3];
+    v3addscl(c, gpos + 3 * g2, ax, s ? -h : h);
+    v3add(c, c, rim);
+    v3sub(d, c, gpos + 3 * g1);
+    double dist = v3dot(d, n);
+    if (dist >= margin) continue;
+    v3addscl(out.pos[out.n], c, n, -0.5 * dist);
+    out.dist[out.n] = dist; out.n++;
+  }
+}
 __device__ __noinline__ void col_plane_box(const double* ws, int g1, int g2, double margin, PairContacts& out) {
   const DevModel& m = c_m; const Layout& L = c_L;
   const double *gpos = ws + L.gpos, *gmat = ws + L.gmat;
@@ -646,11 +755,11 @@ __device__ __noinline__ int stage_collision(double* ws, int* wi, int lane, int* 
     unsigned mask = __ballot_sync(FULL, pass);
     if (pass) {
       int pos = ncand + __popc(mask & ((1u << lane) - 1));
-      if (pos < GE_MAXCAND) cand[pos] = p;
+      if (pos < L.maxcand) cand[pos] = p;
     }
     ncand += __popc(mask);
   }
-  if (ncand > GE_MAXCAND) { ncand = GE_MAXCAND; *status |= 1; }
+  if (ncand > L.maxcand) { ncand = L.maxcand; *status |= 1; }
   __syncwarp();
   double* con = ws + L.con;
   int *cb1 = wi + L.i_cb1, *cb2 = wi + L.i_cb2, *cdim = wi + L.i_cdim, *cpair = wi + L.i_cpair;
@@ -669,9 +778,14 @@ __device__ __noinline__ int stage_collision(double* ws, int* wi, int lane, int* 
         if (t2 == G_SPHERE) col_plane_sphere(ws, g1, g2, margin, pc);
         else if (t2 == G_BOX) col_plane_box(ws, g1, g2, margin, pc);
         else if (t2 == G_MESH) col_plane_mesh(ws, g1, g2, margin, pc);
+        else if (t2 == G_CAPSULE) col_plane_capsule(ws, g1, g2, margin, pc);
+        else if (t2 == G_CYLINDER) col_plane_cylinder(ws, g1, g2, margin, pc);
       } else if (t1 == G_SPHERE && t2 == G_SPHERE) col_sphere_sphere(ws, g1, g2, margin, pc);
       else if (t1 == G_SPHERE && t2 == G_BOX) col_sphere_box(ws, g1, g2, margin, pc);
       else if (t1 == G_BOX && t2 == G_BOX) col_box_box(ws, g1, g2, margin, pc);
+      else if (t1 == G_SPHERE && t2 == G_CAPSULE) col_sphere_capsule(ws, g1, g2, margin, pc);
+      else if (t1 == G_SPHERE && t2 == G_CYLINDER) col_sphere_cylinder(ws, g1, g2, margin, pc);
+      else if (t1 == G_CAPSULE && t2 == G_CAPSULE) col_capsule_capsule(ws, g1, g2, margin, pc);
     }
     // ordered compaction of the per-lane contact lists
     int off = pc.n;
@@ -681,26 +795,27 @@ __device__ __noinline__ int stage_collision(double* ws, int* wi, int lane, int* 
     off = ncon + off - pc.n;
     for (int k = 0; k < pc.n; k++) {
       int idx = off + k;
-      if (idx >= GE_MAXCON) break;
+      if (idx >= L.maxcon) break;
       double* c = con + idx * L.cstride;
       c[C_DIST] = pc.dist[k]; v3copy(c + C_POS, pc.pos[k]); v3copy(c + C_FRAME, pc.normal);
       cpair[idx] = p;
     }
     ncon += total;
   }
-  if (ncon > GE_MAXCON) { ncon = GE_MAXCON; *status |= 1; }
+  if (ncon > L.maxcon) { ncon = L.maxcon; *status |= 1; }
   __syncwarp();
   // ---- convex pairs through MPR
   for (int ci = 0; ci < ncand; ci++) {
     int p = cand[ci];
     int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1], t1 = m.geom_type[g1], t2 = m.geom_type[g2];
-    bool analytic = (t1 == G_PLANE) || (t1 == G_SPHERE && (t2 == G_SPHERE || t2 == G_BOX)) || (t1 == G_BOX && t2 == G_BOX);
+    bool analytic = (t1 == G_PLANE) || (t1 == G_SPHERE && (t2 == G_SPHERE || t2 == G_BOX || t2 == G_CAPSULE || t2 == G_CYLINDER)) ||
+                    (t1 == G_BOX && t2 == G_BOX) || (t1 == G_CAPSULE && t2 == G_CAPSULE);
     if (analytic) continue;
     double margin = m.pair_margin[p], depth, dir[3], pos[3];
     if (!mpr_w(ws, g1, g2, 0.5 * margin, &depth, dir, pos, lane)) continue;
     double dist = margin - depth;
     if (dist >= margin) continue;
-    if (ncon >= GE_MAXCON) { *status |= 1; break; }
+    if (ncon >= L.maxcon) { *status |= 1; break; }
     if (lane == 0) {
       double* c = con + ncon * L.cstride;
       c[C_DIST] = dist; v3copy(c + C_POS, pos); v3copy(c + C_FRAME, dir);

@@ -85,6 +85,48 @@ __device__ __forceinline__ double ray_geom(int g, const double* fr, const double
     if (tn <= 0) return -1;
     m3mulv(nrm, R, nl);
     return tn;
+  } else if (type == G_CYLINDER) {  // infinite cylinder and the slab |z| <= h, intersected like the box slabs
+    double r = size[0], h = size[1];
+    double a = dl[0] * dl[0] + dl[1] * dl[1], b = ol[0] * dl[0] + ol[1] * dl[1], c = ol[0] * ol[0] + ol[1] * ol[1] - r * r;
+    if (a < 1e-14) { if (c > 0) return -1; }
+    else {
+      double disc = b * b - a * c;
+      if (disc < 0) return -1;
+      double sq = sqrt(disc);
+      tn = (-b - sq) / a; tf = (-b + sq) / a;
+      v3set(nl, (ol[0] + tn * dl[0]) / r, (ol[1] + tn * dl[1]) / r, 0);
+    }
+    if (fabs(dl[2]) < 1e-14) { if (fabs(ol[2]) > h) return -1; }
+    else {
+      double t1 = (-h - ol[2]) / dl[2], t2 = (h - ol[2]) / dl[2], s = -1;
+      if (t1 > t2) { double x = t1; t1 = t2; t2 = x; s = 1; }
+      if (t1 > tn) { tn = t1; v3set(nl, 0, 0, s); }
+      if (t2 < tf) tf = t2;
+    }
+    if (tn > tf || tn <= 0) return -1;
+    m3mulv(nrm, R, nl);
+    return tn;
+  } else if (type == G_CAPSULE) {  // side wall where |z| <= h, otherwise the outward half of either end sphere
+    double r = size[0], h = size[1], best = -1;
+    double a = dl[0] * dl[0] + dl[1] * dl[1], b = ol[0] * dl[0] + ol[1] * dl[1], c = ol[0] * ol[0] + ol[1] * ol[1] - r * r;
+    if (a >= 1e-14) {
+      double disc = b * b - a * c;
+      if (disc >= 0) {
+        double t1 = (-b - sqrt(disc)) / a, z = ol[2] + t1 * dl[2];
+        if (t1 > 0 && fabs(z) <= h) { best = t1; v3set(nl, (ol[0] + t1 * dl[0]) / r, (ol[1] + t1 * dl[1]) / r, 0); }
+      }
+    }
+    for (int s = 0; s < 2; s++) {
+      double sg = s ? -1.0 : 1.0, oc[3] = {ol[0], ol[1], ol[2] - sg * h};
+      double bb = v3dot(oc, dl), cc = v3dot(oc, oc) - r * r, aa = v3dot(dl, dl), disc = bb * bb - aa * cc;
+      if (disc < 0) continue;
+      double t1 = (-bb - sqrt(disc)) / aa;
+      if (t1 <= 0 || sg * (oc[2] + t1 * dl[2]) < 0) continue;
+      if (best < 0 || t1 < best) { best = t1; v3addscl(nl, oc, dl, t1); v3scl(nl, nl, 1.0 / r); }
+    }
+    if (best <= 0) return -1;
+    m3mulv(nrm, R, nl);
+    return best;
   }
   return -1;
 }
@@ -172,8 +214,8 @@ static inline int render_launch(RenderCtx& rc, const DevModel& m, const Layout& 
     rc.cap_envs = n_env;
   }
   static bool attr_done = false;
-  if (!attr_done && L.total_bytes > 48 * 1024) { cudaFuncSetAttribute(k_render_fk, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes); attr_done = true; }
-  k_render_fk<<<n_env, 32, L.total_bytes, stream>>>(qpos, n_env, rc.gframes);
+  if (!attr_done && L.fk_bytes > 48 * 1024) { cudaFuncSetAttribute(k_render_fk, cudaFuncAttributeMaxDynamicSharedMemorySize, L.fk_bytes); attr_done = true; }
+  k_render_fk<<<n_env, 32, L.fk_bytes, stream>>>(qpos, n_env, rc.gframes);
   int tiles = ((W + RTILE - 1) / RTILE) * ((H + RTILE - 1) / RTILE);
   dim3 grid(tiles, n_env), blk(RTILE, RTILE);
   k_render<<<grid, blk, 0, stream>>>(rc.gframes, n_env, cam, W, H, rgb, depth);

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) k_run(EnvArrays E, int n_env, int nsub, d
   p.phase = valid ? E.prog_phase[env] : PH_NONE;
   bool busy = c.active || p.phase != PH_NONE;
   if (!__syncthreads_or(busy)) return;
-  double* ws = smem + (size_t)threadIdx.y * (L.total_bytes / 8);
+  double* ws = L.ws_global ? E.gws + (size_t)(valid ? env : 0) * (L.total_bytes / 8) : smem + (size_t)threadIdx.y * (L.total_bytes / 8);
   int* wi = (int*)(ws + L.total_doubles);
   int info[12];
   unsigned char reward = 0;
@@ -103,8 +103,8 @@ __global__ void __launch_bounds__(32) k_debug(EnvArrays E, int env, int field, d
   extern __shared__ double smem[];
   const DevModel& m = c_m; const Layout& L = c_L;
   int lane = threadIdx.x;
-  double* ws = smem;
-  int* wi = (int*)(smem + L.total_doubles);
+  double* ws = L.ws_global ? E.gws + (size_t)env * (L.total_bytes / 8) : smem;
+  int* wi = (int*)(ws + L.total_doubles);
   LANE_LOOP(i, m.nq) ws[L.qpos + i] = E.qpos[(size_t)env * m.nq + i];
   LANE_LOOP(i, m.nv) { ws[L.qvel + i] = E.qvel[(size_t)env * m.nv + i]; ws[L.qaccws + i] = E.qaccws[(size_t)env * m.nv + i]; }
   ws[L.ctl + lane] = E.ctl[(size_t)env * 32 + lane];
@@ -243,6 +243,7 @@ struct ge_engine {
   cudaStream_t stream;
   DevModel hm;       // host copy of the struct holding DEVICE pointers
   Layout lay;
+  size_t ws_smem;    // dynamic shared memory per env of the stepping kernels (0: workspace in HBM)
   EnvArrays E;
   void* dblob;       // whole blob on the device
   std::vector<char> hblob;
@@ -271,6 +272,9 @@ static int64_t blob_off(const std::vector<char>& b, const char* name) {
   return p ? (const char*)p - b.data() : -1;
 }
 
+struct ge_engine;
+static ge_engine* g_bound = nullptr;  // engine whose model / layout currently sit in __constant__ memory
+
 static int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
 static void make_layout(const DevModel& m, Layout& L, const int* tree_dofnum_h, const int* tree_simple_h, int ntree_dofnum_n) {
@@ -287,7 +291,10 @@ static void make_layout(const DevModel& m, Layout& L, const int* tree_dofnum_h, 
   L.qfrc_smooth = take(nv); L.qacc_smooth = take(nv); L.qfrc_constraint = take(nv); L.qacc = take(nv);
   L.Ma = take(nv); L.grad = take(nv); L.search = take(nv); L.Mv = take(nv);
   L.cstride = align_up(C_MU + 4 * m.maxdim - 1, 2);
-  L.con = take(GE_MAXCON * L.cstride);
+  // list capacities: the 6-object scene never exceeded 20 contacts; piles of free objects need room for ~3 contacts per object
+  L.maxcon = m.ntree <= 8 ? 32 : 128;
+  L.maxcand = 2 * L.maxcon;
+  L.con = take(L.maxcon * L.cstride);
   L.sr = take(6 * GE_MAXSR);
   L.scratch = o;
   // phase A (kinematics/dynamics/collision)
@@ -321,13 +328,15 @@ static void make_layout(const DevModel& m, Layout& L, const int* tree_dofnum_h, 
   int end = endA1 > endA2 ? endA1 : endA2;
   if (endB > end) end = endB;
   L.total_doubles = align_up(end, 2);
+  L.fk_bytes = align_up(endA1, 2) * 8;
   int io = 0;
   auto takeI = [&](int n) { int r = io; io += n; return r; };
-  L.i_cb1 = takeI(GE_MAXCON); L.i_cb2 = takeI(GE_MAXCON); L.i_ct1 = takeI(GE_MAXCON); L.i_ct2 = takeI(GE_MAXCON); L.i_cdim = takeI(GE_MAXCON); L.i_cpair = takeI(GE_MAXCON); L.i_cact = takeI(GE_MAXCON);
+  L.i_cb1 = takeI(L.maxcon); L.i_cb2 = takeI(L.maxcon); L.i_ct1 = takeI(L.maxcon); L.i_ct2 = takeI(L.maxcon); L.i_cdim = takeI(L.maxcon); L.i_cpair = takeI(L.maxcon); L.i_cact = takeI(L.maxcon);
   L.i_srA = takeI(GE_MAXSR); L.i_srB = takeI(GE_MAXSR); L.i_srtype = takeI(GE_MAXSR); L.i_sract = takeI(GE_MAXSR);
-  L.i_cand = takeI(GE_MAXCAND); L.i_first = takeI(nv); L.i_tcoupled = takeI(m.ntree); L.i_tcount = takeI(m.ntree); L.i_tlist = takeI(m.ntree * 16); L.i_misc = takeI(8);
+  L.i_cand = takeI(L.maxcand); L.i_first = takeI(nv); L.i_tcoupled = takeI(m.ntree); L.i_tcount = takeI(m.ntree); L.i_tlist = takeI(m.ntree * GE_TLIST); L.i_misc = takeI(8);
   L.total_ints = align_up(io, 4);
   L.total_bytes = L.total_doubles * 8 + L.total_ints * 4;
+  L.ws_global = 0;
 }
 
 extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int device, void* stream, ge_handle* out) {
@@ -389,11 +398,17 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
     memcpy(h->base_pos, bp, 24);
   }
   make_layout(m, h->lay, (const int*)blob_find(B, "tree_dofnum", nullptr), (const int*)blob_find(B, "tree_simple", nullptr), m.ntree);
+  // workspace placement: shared memory when one env fits a CTA's 227 KB, else one row per env in HBM (L1/L2-cached); GE_WS_GLOBAL=1
+  // forces the HBM placement (used by the tests to cover that path with the small scene)
+  h->lay.ws_global = h->lay.total_bytes > 227 * 1024 ? 1 : 0;
+  if (const char* ev = getenv("GE_WS_GLOBAL")) if (atoi(ev) != 0) h->lay.ws_global = 1;
+  if (h->lay.fk_bytes > 227 * 1024) { cudaFree(h->dblob); delete h; return fail(GE_ERR_MODEL, "model too large: kinematics workspace exceeds shared memory"); }
   CK(cudaMemcpyToSymbol(c_m, &m, sizeof m));
   CK(cudaMemcpyToSymbol(c_L, &h->lay, sizeof(Layout)));
   // warps (= envs) per CTA: maximise the resident warps per SM (228 KB shared memory per SM, 1 KB reserved per CTA, 227 KB max per
   // CTA); ties go to the smaller CTA (less barrier imbalance).  r01 sweeps are in DESIGN.md; GE_WPB overrides.
-  {
+  if (h->lay.ws_global) h->wpb = 4;
+  else {
     int best = 1, best_warps = 0;
     for (int w = 1; w <= 8; w++) {
       long per_cta = (long)w * h->lay.total_bytes;
@@ -406,13 +421,13 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
   }
   h->stage_sync = 1;
   if (const char* ev = getenv("GE_STAGE_SYNC")) h->stage_sync = atoi(ev) != 0;
-  if (const char* ev = getenv("GE_WPB")) { int v = atoi(ev); if (v >= 1 && v <= 8 && v * h->lay.total_bytes <= 227 * 1024) h->wpb = v; }
-  if (h->wpb < 1) { cudaFree(h->dblob); delete h; return fail(GE_ERR_MODEL, "model too large for the per-warp shared-memory workspace"); }
-  CK(cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, h->wpb * h->lay.total_bytes));
-  if (h->lay.total_bytes > 48 * 1024) {
-    CK(cudaFuncSetAttribute(k_debug, cudaFuncAttributeMaxDynamicSharedMemorySize, h->lay.total_bytes));
-    CK(cudaFuncSetAttribute(k_body_xpos, cudaFuncAttributeMaxDynamicSharedMemorySize, h->lay.total_bytes));
+  if (const char* ev = getenv("GE_WPB")) { int v = atoi(ev); if (v >= 1 && v <= 8 && (h->lay.ws_global || v * h->lay.total_bytes <= 227 * 1024)) h->wpb = v; }
+  h->ws_smem = h->lay.ws_global ? 0 : (size_t)h->lay.total_bytes;
+  if (h->ws_smem) {
+    CK(cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, h->wpb * h->lay.total_bytes));
+    if (h->lay.total_bytes > 48 * 1024) CK(cudaFuncSetAttribute(k_debug, cudaFuncAttributeMaxDynamicSharedMemorySize, h->lay.total_bytes));
   }
+  if (h->lay.fk_bytes > 48 * 1024) CK(cudaFuncSetAttribute(k_body_xpos, cudaFuncAttributeMaxDynamicSharedMemorySize, h->lay.fk_bytes));
   EnvArrays& E = h->E;
   size_t N = n_envs;
 #define AL(ptr, type, cnt) CK(cudaMalloc(&ptr, sizeof(type) * (cnt))); CK(cudaMemset(ptr, 0, sizeof(type) * (cnt)))
@@ -421,6 +436,8 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
   AL(E.prog_phase, int, N); AL(E.prog_rot, int, N); AL(E.prog_grasp, int, N); AL(E.prog_aux, int, N); AL(E.prog_info, int, N * 12);
   AL(E.prog_coords, double, N * 3); AL(E.prog_table, double, N); AL(E.reward, unsigned char, N); AL(E.status, int, N); AL(E.substeps, long long, N);
   AL(E.busy_count, int, 1);
+  E.gws = nullptr;
+  if (h->lay.ws_global) { AL(E.gws, double, N * (size_t)(h->lay.total_bytes / 8)); }
   AL(h->d_nout, int, 1); AL(h->d_dbg, double, 1 << 16);
 #undef AL
   render_init(h->rctx, m, h->hblob.data());
@@ -438,6 +455,7 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
     CK(cudaStreamSynchronize(h->stream));
     cudaFree(dq);
   }
+  g_bound = h;
   *out = h;
   return GE_OK;
 }
@@ -445,10 +463,12 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
 extern "C" int ge_destroy(ge_handle h) {
   if (!h) return GE_OK;
   cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  if (g_bound == h) g_bound = nullptr;
   EnvArrays& E = h->E;
   void* ptrs[] = {E.qpos, E.qvel, E.qaccws, E.ctl, E.cmd_mask, E.cmd_maxsteps, E.cmd_steps, E.cmd_result, E.cmd_active, E.cmd_tol, E.prog_phase,
                   E.prog_rot, E.prog_grasp, E.prog_aux, E.prog_info, E.prog_coords, E.prog_table, E.reward, E.status, E.substeps, E.busy_count,
-                  h->d_nout, h->d_dbg, h->dblob};
+                  h->d_nout, h->d_dbg, h->dblob, E.gws};
   for (void* p : ptrs) cudaFree(p);
   render_free(h->rctx);
   delete h;
@@ -459,14 +479,21 @@ extern "C" int ge_size(ge_handle h, int what) {
   if (!h) return GE_ERR_ARG;
   switch (what) {
     case 0: return h->hm.nq; case 1: return h->hm.nv; case 2: return h->hm.nbody; case 3: return h->hm.ngeom; case 4: return h->hm.nu;
-    case 5: return h->n_envs; case 6: return GE_MAXCON; case 7: return h->lay.total_bytes; case 8: return h->wpb;
+    case 5: return h->n_envs; case 6: return h->lay.maxcon; case 7: return h->lay.total_bytes; case 8: return h->wpb; case 9: return h->lay.ws_global;
   }
   return GE_ERR_ARG;
 }
 
+// The model / layout live in __constant__ memory of this module.  Engines of different scenes may coexist in one process:
+// the constants are re-uploaded (after draining the device) whenever a call arrives for an engine other than the last one used.
 static int bind(ge_handle h) {
-  // the model / layout live in __constant__ memory of this module: one active model per process and device
   CK(cudaSetDevice(h->device));
+  if (g_bound != h) {
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyToSymbol(c_m, &h->hm, sizeof(DevModel)));
+    CK(cudaMemcpyToSymbol(c_L, &h->lay, sizeof(Layout)));
+    g_bound = h;
+  }
   return GE_OK;
 }
 
@@ -489,7 +516,7 @@ extern "C" int ge_get_state(ge_handle h, double* qpos, double* qvel) {
 extern "C" int ge_get_body_xpos(ge_handle h, double* xpos) {
   if (!h || !xpos) return GE_ERR_ARG;
   if (bind(h)) return GE_ERR_CUDA;
-  k_body_xpos<<<h->n_envs, 32, h->lay.total_bytes, h->stream>>>(h->E, h->n_envs, xpos);
+  k_body_xpos<<<h->n_envs, 32, h->lay.fk_bytes, h->stream>>>(h->E, h->n_envs, xpos);
   h->launches++;
   CK(cudaGetLastError());
   return GE_OK;
@@ -532,7 +559,7 @@ extern "C" int ge_run_async(ge_handle h, int substeps) {
   if (!h || substeps <= 0) return fail(GE_ERR_ARG, "ge_run_async: bad argument");
   if (bind(h)) return GE_ERR_CUDA;
   dim3 blk(32, h->wpb);
-  k_run<<<(h->n_envs + h->wpb - 1) / h->wpb, blk, (size_t)h->wpb * h->lay.total_bytes, h->stream>>>(h->E, h->n_envs, substeps, h->base_pos[0], h->base_pos[1],
+  k_run<<<(h->n_envs + h->wpb - 1) / h->wpb, blk, (size_t)h->wpb * h->ws_smem, h->stream>>>(h->E, h->n_envs, substeps, h->base_pos[0], h->base_pos[1],
                                                                                                    h->base_pos[2], h->stage_sync);
   h->launches++; h->substep_launches++;
   CK(cudaGetLastError());
@@ -635,7 +662,7 @@ extern "C" int ge_debug_forward(ge_handle h, int env, const char* field, double*
   for (int i = 0; i < 12; i++) if (!strcmp(names[i], field)) f = i;
   if (f < 0) return fail(GE_ERR_ARG, "ge_debug_forward: unknown field %s", field);
   if (cap > (1 << 16)) cap = 1 << 16;
-  k_debug<<<1, 32, h->lay.total_bytes, h->stream>>>(h->E, env, f, h->d_dbg, cap, h->d_nout);
+  k_debug<<<1, 32, h->ws_smem, h->stream>>>(h->E, env, f, h->d_dbg, cap, h->d_nout);
   h->launches++;
   CK(cudaGetLastError());
   int n = 0;

@@ -91,6 +91,11 @@ class BatchedEngine:
         self.nq, self.nv, self.nbody, self.ngeom, self.nu = [self.L.ge_size(h, k) for k in range(5)]
         self.smem_bytes = self.L.ge_size(h, 7)
 
+    def size(self, what):
+        """ge_size: 0 nq, 1 nv, 2 nbody, 3 ngeom, 4 nu, 5 n_envs, 6 max contacts, 7 workspace bytes per env, 8 envs per CTA,
+        9 workspace placement (0 shared memory, 1 HBM rows)"""
+        return int(self.L.ge_size(self.h, int(what)))
+
     # ------------------------------------------------------------------ helpers
     def _ck(self, r, what):
         if r < 0:

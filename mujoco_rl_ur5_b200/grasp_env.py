@@ -7,7 +7,8 @@ Same constructor keywords, `reset()`, `step(action, record_grasps=False, markers
 `BatchedGraspEnv` for throughput.
 
 Deviations from the reference, all documented in DESIGN.md: deterministic `stay` / PID period, analytic IK
-(A.4), scene A by default (the engine does not cover the 40-object scene yet), no viewer / cv2 windows.
+(A.4), the 6-object scene when no file is given (GRASP_SCENE=B or file=...many_objects.xml selects the reference's default
+40-object scene), no viewer / cv2 windows.
 """
 import copy
 import math
@@ -16,7 +17,7 @@ from collections import defaultdict
 
 import numpy as np
 
-from .batched_env import HOME, ROTATIONS, scene_a_reset_qpos
+from .batched_env import HOME, ROTATIONS, scene_b_reset_qpos
 from .controller import MJ_Controller, _Model, colored
 from .engine import BatchedEngine
 from .model.scene import load_scene, load_scene_blob
@@ -34,10 +35,7 @@ def _scene_key(file):
     if file is None:
         return os.environ.get("GRASP_SCENE", "A")
     name = os.path.basename(str(file))
-    if "many_objects" in name:
-        raise NotImplementedError("UR5gripper_2_finger_many_objects.xml (40 free objects, condim 6) is not covered by the engine yet; "
-                                  "use UR5gripper_2_finger.xml (scene A)")
-    return "A"
+    return "B" if "many_objects" in name else "A"
 
 
 class GraspEnv(utils.EzPickle):
@@ -165,7 +163,11 @@ class GraspEnv(utils.EzPickle):
         return self.reset_model()
 
     def reset_model(self, show_obs=True):
-        """Scene-A reset (IT4 rule, GraspingEnv.py:435-463) drawn from numpy's GLOBAL RNG like the reference (Q8)."""
+        """Object randomisation drawn from numpy's GLOBAL RNG like the reference (Q8): the live 40-object rule of
+        GraspingEnv.py:418-430 for the many-objects scene, the IT4 rule (:435-463) for the 6-object scene."""
+        if self.scene == "B":
+            q = scene_b_reset_qpos(self.arrays)
+            return self._finish_reset(q)
         q = np.array(self.arrays["qpos0"], dtype=np.float64).copy()
         q[:7] = HOME
         q[7] = HOME[6]
@@ -177,6 +179,9 @@ class GraspEnv(utils.EzPickle):
             a = 8 + 7 * i
             q[a], q[a + 1], q[a + 2] = xs[i], ys[i], 0.0
             q[a + 3:a + 7] = [1, 0, 0, 0]
+        return self._finish_reset(q)
+
+    def _finish_reset(self, q):
         self.set_state(q, np.zeros(int(self.arrays["nv"][0])))
         self.controller.set_group_joint_target(group="All", target=q[self.controller.actuated_joint_ids])
         self.controller.stay(1000, render=self.render)

@@ -491,6 +491,42 @@ static void col_plane_mesh(Env* e, int pair, int g1, int g2) { /* DECISION: deep
   v3addscl(pos, w, n, -0.5 * dist);
   add_contact(e, pair, dist, pos, n);
 }
+/* plane vs capsule: the two end spheres (+axis end first).  plane vs cylinder (DECISION: MuJoCo's mjc_PlaneCylinder is not
+ * documented): the deepest rim point of each cap (+axis cap first); a cap parallel to the plane contributes its centre. */
+static void col_plane_capsule(Env* e, int pair, int g1, int g2) {
+  const Model* m = e->m;
+  double n[3], ax[3];
+  m3col(n, e->gmat + 9 * g1, 2); m3col(ax, e->gmat + 9 * g2, 2);
+  double r = m->geom_size[3 * g2], h = m->geom_size[3 * g2 + 1];
+  for (int s = 0; s < 2; s++) {
+    double c[3], d[3], pos[3];
+    v3addscl(c, e->gpos + 3 * g2, ax, s ? -h : h);
+    v3sub(d, c, e->gpos + 3 * g1);
+    double dist = v3dot(d, n) - r;
+    if (dist >= m->pair_margin[pair]) continue;
+    v3addscl(pos, c, n, -(r + 0.5 * dist));
+    add_contact(e, pair, dist, pos, n);
+  }
+}
+static void col_plane_cylinder(Env* e, int pair, int g1, int g2) {
+  const Model* m = e->m;
+  double n[3], ax[3], rim[3];
+  m3col(n, e->gmat + 9 * g1, 2); m3col(ax, e->gmat + 9 * g2, 2);
+  double r = m->geom_size[3 * g2], h = m->geom_size[3 * g2 + 1];
+  v3addscl(rim, n, ax, -v3dot(n, ax)); /* component of the plane normal perpendicular to the axis */
+  double len = v3norm(rim);
+  if (len > 1e-6) v3scl(rim, rim, -r / len); else v3set(rim, 0, 0, 0);
+  for (int s = 0; s < 2; s++) {
+    double c[3], d[3], pos[3];
+    v3addscl(c, e->gpos + 3 * g2, ax, s ? -h : h);
+    v3add(c, c, rim);
+    v3sub(d, c, e->gpos + 3 * g1);
+    double dist = v3dot(d, n);
+    if (dist >= m->pair_margin[pair]) continue;
+    v3addscl(pos, c, n, -0.5 * dist);
+    add_contact(e, pair, dist, pos, n);
+  }
+}
 static void col_sphere_sphere(Env* e, int pair, int g1, int g2) {
   const Model* m = e->m;
   double d[3];
@@ -501,6 +537,73 @@ static void col_sphere_sphere(Env* e, int pair, int g1, int g2) {
   double pos[3];
   v3addscl(pos, e->gpos + 3 * g1, d, r1 + 0.5 * dist);
   add_contact(e, pair, dist, pos, d);
+}
+/* sphere vs capsule, capsule vs capsule, sphere vs cylinder: closed forms (MuJoCo also treats these pairs analytically; MPR on two
+ * smooth surfaces converges slowly and its portal choice is ill-conditioned).  Normal points from geom1 to geom2. */
+static void col_sphere_capsule(Env* e, int pair, int g1, int g2) {
+  const Model* m = e->m;
+  const double *c = e->gpos + 3 * g1, *p = e->gpos + 3 * g2;
+  double ax[3], d[3], q[3], n[3], pos[3];
+  m3col(ax, e->gmat + 9 * g2, 2);
+  double r1 = m->geom_size[3 * g1], r2 = m->geom_size[3 * g2], h = m->geom_size[3 * g2 + 1];
+  v3sub(d, c, p);
+  double t = v3dot(d, ax);
+  if (t > h) t = h; else if (t < -h) t = -h;
+  v3addscl(q, p, ax, t); v3sub(d, q, c);
+  double len = v3norm(d);
+  if (len < 1e-12) { m3col(n, e->gmat + 9 * g2, 0); len = 0; } else v3scl(n, d, 1.0 / len);
+  double dist = len - r1 - r2;
+  if (dist >= m->pair_margin[pair]) return;
+  v3addscl(pos, c, n, r1 + 0.5 * dist);
+  add_contact(e, pair, dist, pos, n);
+}
+static void col_capsule_capsule(Env* e, int pair, int g1, int g2) {
+  const Model* m = e->m;
+  const double *p1 = e->gpos + 3 * g1, *p2 = e->gpos + 3 * g2;
+  double a1[3], a2[3], w[3], q1[3], q2[3], d[3], n[3], pos[3];
+  m3col(a1, e->gmat + 9 * g1, 2); m3col(a2, e->gmat + 9 * g2, 2);
+  double r1 = m->geom_size[3 * g1], h1 = m->geom_size[3 * g1 + 1], r2 = m->geom_size[3 * g2], h2 = m->geom_size[3 * g2 + 1];
+  v3sub(w, p1, p2);
+  double b = v3dot(a1, a2), dd = v3dot(a1, w), ee = v3dot(a2, w), den = 1.0 - b * b, s, t;
+  if (den < 1e-10) { /* parallel axes: middle of the overlap of the two segments (measured along axis 1) */
+    double c2 = -dd, lo = c2 - h2, hi = c2 + h2; /* segment 2 projected on axis 1: centre -dd, half length h2 */
+    if (lo < -h1) lo = -h1;
+    if (hi > h1) hi = h1;
+    s = lo <= hi ? 0.5 * (lo + hi) : (c2 > 0 ? h1 : -h1);
+  } else {
+    s = (b * ee - dd) / den;
+    if (s > h1) s = h1; else if (s < -h1) s = -h1;
+  }
+  t = b * s + ee;
+  if (t > h2) t = h2; else if (t < -h2) t = -h2;
+  s = b * t - dd; /* re-project onto segment 1 with t fixed */
+  if (s > h1) s = h1; else if (s < -h1) s = -h1;
+  v3addscl(q1, p1, a1, s); v3addscl(q2, p2, a2, t); v3sub(d, q2, q1);
+  double len = v3norm(d);
+  if (len < 1e-12) { v3cross(n, a1, a2); if (v3norm(n) < 1e-12) m3col(n, e->gmat + 9 * g1, 0); v3normalize(n); len = 0; } else v3scl(n, d, 1.0 / len);
+  double dist = len - r1 - r2;
+  if (dist >= m->pair_margin[pair]) return;
+  v3addscl(pos, q1, n, r1 + 0.5 * dist);
+  add_contact(e, pair, dist, pos, n);
+}
+static void col_sphere_cylinder(Env* e, int pair, int g1, int g2) {
+  const Model* m = e->m;
+  const double *c = e->gpos + 3 * g1, *R = e->gmat + 9 * g2;
+  double t[3], l[3], out[3], n[3], pos[3];
+  v3sub(t, c, e->gpos + 3 * g2); m3Tmulv(l, R, t);
+  double r1 = m->geom_size[3 * g1], r = m->geom_size[3 * g2], h = m->geom_size[3 * g2 + 1];
+  double rho = sqrt(l[0] * l[0] + l[1] * l[1]), sz = l[2] >= 0 ? 1.0 : -1.0, dz = fabs(l[2]) - h, dr = rho - r, sd;
+  double ux = rho > 1e-12 ? l[0] / rho : 1.0, uy = rho > 1e-12 ? l[1] / rho : 0.0;
+  if (dz <= 0 && dr <= 0) {
+    if (dr > dz) { v3set(out, ux, uy, 0); sd = dr; } else { v3set(out, 0, 0, sz); sd = dz; }
+  } else if (dz <= 0) { v3set(out, ux, uy, 0); sd = dr; }
+  else if (dr <= 0) { v3set(out, 0, 0, sz); sd = dz; }
+  else { sd = sqrt(dr * dr + dz * dz); v3set(out, dr * ux / sd, dr * uy / sd, sz * dz / sd); }
+  double dist = sd - r1;
+  if (dist >= m->pair_margin[pair]) return;
+  m3mulv(n, R, out); v3scl(n, n, -1.0);
+  v3addscl(pos, c, n, r1 + 0.5 * dist);
+  add_contact(e, pair, dist, pos, n);
 }
 static void col_sphere_box(Env* e, int pair, int g1, int g2) {
   const Model* m = e->m;
@@ -783,7 +886,8 @@ static void col_convex(Env* e, int pair, int g1, int g2) {
 }
 
 static int pair_is_analytic(int t1, int t2) {
-  return t1 == G_PLANE || (t1 == G_SPHERE && (t2 == G_SPHERE || t2 == G_BOX)) || (t1 == G_BOX && t2 == G_BOX);
+  return t1 == G_PLANE || (t1 == G_SPHERE && (t2 == G_SPHERE || t2 == G_BOX || t2 == G_CAPSULE || t2 == G_CYLINDER)) || (t1 == G_BOX && t2 == G_BOX) ||
+         (t1 == G_CAPSULE && t2 == G_CAPSULE);
 }
 /* Two passes over the static candidate list: analytic pair functions first, then the generic convex (MPR) pairs.
  * (Contact order only affects floating-point summation order in the solver; the CUDA engine emits the same order.) */
@@ -803,7 +907,8 @@ static void collision(Env* e) {
       if (t2 == G_SPHERE) col_plane_sphere(e, p, g1, g2);
       else if (t2 == G_BOX) col_plane_box(e, p, g1, g2);
       else if (t2 == G_MESH) col_plane_mesh(e, p, g1, g2);
-      else { /* plane vs capsule / cylinder: not needed by scene A */ }
+      else if (t2 == G_CAPSULE) col_plane_capsule(e, p, g1, g2);
+      else if (t2 == G_CYLINDER) col_plane_cylinder(e, p, g1, g2);
       continue;
     }
     m3mulv(t, e->gmat + 9 * g1, m->geom_obbcenter + 3 * g1); v3add(c1, e->gpos + 3 * g1, t);
@@ -816,6 +921,9 @@ static void collision(Env* e) {
     if (t1 == G_SPHERE && t2 == G_SPHERE) col_sphere_sphere(e, p, g1, g2);
     else if (t1 == G_SPHERE && t2 == G_BOX) col_sphere_box(e, p, g1, g2);
     else if (t1 == G_BOX && t2 == G_BOX) col_box_box(e, p, g1, g2);
+    else if (t1 == G_SPHERE && t2 == G_CAPSULE) col_sphere_capsule(e, p, g1, g2);
+    else if (t1 == G_SPHERE && t2 == G_CYLINDER) col_sphere_cylinder(e, p, g1, g2);
+    else if (t1 == G_CAPSULE && t2 == G_CAPSULE) col_capsule_capsule(e, p, g1, g2);
     else col_convex(e, p, g1, g2);
   }
 }
@@ -1395,7 +1503,51 @@ static double ray_geom(const Env* e, int g, const double* o, const double* dir, 
     m3mulv(nrm, R, nl);
     return tn;
   }
-  return -1; /* capsule / cylinder: scene B only, not rendered by the oracle yet */
+  if (type == G_CYLINDER) { /* infinite cylinder and the slab |z| <= h, intersected like the box slabs */
+    double r = size[0], h = size[1];
+    double a = dl[0] * dl[0] + dl[1] * dl[1], b = ol[0] * dl[0] + ol[1] * dl[1], c = ol[0] * ol[0] + ol[1] * ol[1] - r * r;
+    if (a < 1e-14) { if (c > 0) return -1; }
+    else {
+      double disc = b * b - a * c;
+      if (disc < 0) return -1;
+      double sq = sqrt(disc);
+      tn = (-b - sq) / a; tf = (-b + sq) / a;
+      v3set(nl, (ol[0] + tn * dl[0]) / r, (ol[1] + tn * dl[1]) / r, 0);
+    }
+    if (fabs(dl[2]) < 1e-14) { if (fabs(ol[2]) > h) return -1; }
+    else {
+      double t1 = (-h - ol[2]) / dl[2], t2 = (h - ol[2]) / dl[2], s = -1;
+      if (t1 > t2) { double x = t1; t1 = t2; t2 = x; s = 1; }
+      if (t1 > tn) { tn = t1; v3set(nl, 0, 0, s); }
+      if (t2 < tf) tf = t2;
+    }
+    if (tn > tf || tn <= 0) return -1;
+    m3mulv(nrm, R, nl);
+    return tn;
+  }
+  if (type == G_CAPSULE) { /* side wall where |z| <= h, otherwise the outward half of either end sphere */
+    double r = size[0], h = size[1], best = -1;
+    double a = dl[0] * dl[0] + dl[1] * dl[1], b = ol[0] * dl[0] + ol[1] * dl[1], c = ol[0] * ol[0] + ol[1] * ol[1] - r * r;
+    if (a >= 1e-14) {
+      double disc = b * b - a * c;
+      if (disc >= 0) {
+        double t1 = (-b - sqrt(disc)) / a, z = ol[2] + t1 * dl[2];
+        if (t1 > 0 && fabs(z) <= h) { best = t1; v3set(nl, (ol[0] + t1 * dl[0]) / r, (ol[1] + t1 * dl[1]) / r, 0); }
+      }
+    }
+    for (int s = 0; s < 2; s++) {
+      double sg = s ? -1.0 : 1.0, oc[3] = {ol[0], ol[1], ol[2] - sg * h};
+      double bb = v3dot(oc, dl), cc = v3dot(oc, oc) - r * r, aa = v3dot(dl, dl), disc = bb * bb - aa * cc;
+      if (disc < 0) continue;
+      double t1 = (-bb - sqrt(disc)) / aa;
+      if (t1 <= 0 || sg * (oc[2] + t1 * dl[2]) < 0) continue;
+      if (best < 0 || t1 < best) { best = t1; v3addscl(nl, oc, dl, t1); v3scl(nl, nl, 1.0 / r); }
+    }
+    if (best <= 0) return -1;
+    m3mulv(nrm, R, nl);
+    return best;
+  }
+  return -1;
 }
 void orc_render(Env* e, int cam, int W, int H, uint8_t* rgb, float* depth) {
   const Model* m = e->m;

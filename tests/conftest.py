@@ -18,3 +18,11 @@ def scene_a():
 
     arrays, names = load_scene("A")
     return load_scene_blob("A"), arrays, names
+
+
+@pytest.fixture(scope="session")
+def scene_b():
+    from mujoco_rl_ur5_b200.model.scene import load_scene, load_scene_blob
+
+    arrays, names = load_scene("B")
+    return load_scene_blob("B"), arrays, names
