@@ -4,7 +4,7 @@
 // only when both of its bodies are dynamic and belong to different trees.  Trees that no such contact (or equality row)
 // touches are "uncoupled": their Hessian block is assembled, factorised and solved by ONE lane each, all such trees in
 // parallel (lane t <-> tree t) with a plain dense left-looking Cholesky.  Only the coupled trees (e.g. arm + grasped object)
-// go through the warp-cooperative skyline routine.  Included by ge_solver.cuh.
+// go through the warp-cooperative routine, one connected component ("island") of coupled trees at a time.  Included by ge_solver.cuh.
 #pragma once
 
 #define HIDX(i, j) (((i) * ((i) + 1)) / 2 + (j))
@@ -44,7 +44,7 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
   const DevModel& m = c_m; const Layout& L = c_L;
   double* H = ws + L.H;
   const double *qM = ws + L.qM, *cdof = ws + L.cdof;
-  int *first = wi + L.i_first, *tcoupled = wi + L.i_tcoupled;
+  int* tcoupled = wi + L.i_tcoupled;
   // ---- which trees are coupled to another tree by an active constraint (trees wider than a lane group take the coupled path too)
   LANE_LOOP(t, m.ntree) tcoupled[t] = m.tree_dofnum[t] > GE_GROUP ? 1 : 0;
   __syncwarp();
@@ -65,7 +65,6 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
     for (int j = root; j <= i; j++) H[HIDX(i, j)] = 0;
     int a = m.dof_Madr[i], k = 0;
     for (int j = i; j >= 0; j = m.dof_parentid[j], k++) H[HIDX(i, j)] = qM[a + k];
-    first[i] = root;
   }
   __syncwarp();
   // ---- per-tree lists of the active contacts that live entirely inside one uncoupled tree (one lane per tree scans the contacts)
@@ -132,35 +131,45 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
   bool any_coupled = false;
   for (int t = 0; t < m.ntree; t++) any_coupled |= tcoupled[t] != 0;
   if (!any_coupled) return;
-  // ---- coupled trees, pass 1: row envelopes (a coupled row reaches down to the lowest dof it shares a contact with) ...
-  for (int ci = 0; ci < ncon; ci++) {
-    if (!wi[L.i_cact + ci]) continue;
-    int b1 = wi[L.i_cb1 + ci], b2 = wi[L.i_cb2 + ci], t1 = wi[L.i_ct1 + ci], t2 = wi[L.i_ct2 + ci];
-    if (!((t1 >= 0 && tcoupled[t1]) || (t2 >= 0 && tcoupled[t2]))) continue;
-    int i1 = m.body_lastdof[b1], i2 = m.body_lastdof[b2], n = 0, mydof = -1, minE = 0x7fffffff;
-    while (i1 != i2) {
-      int e;
-      if (i2 > i1) { e = i2; i2 = m.dof_parentid[i2]; } else { e = i1; i1 = m.dof_parentid[i1]; }
-      if (n == lane) mydof = e;
-      if (e < minE) minE = e;
-      n++;
+  // ---- coupled trees, pass 1: islands.  Trees joined by active contacts / equality rows form connected components; the Hessian
+  // is block diagonal over them (no fill between components), so each island is later factorised on its own dense sub-matrix.
+  // Label propagation: every tree starts with its own index, edges pull both ends to the smaller label until nothing changes
+  // (the fixed point - the smallest tree index of the component - does not depend on the order of the updates).
+  int* island = wi + L.i_island;
+  LANE_LOOP(t, m.ntree) island[t] = t;
+  __syncwarp();
+  for (int iter = 0; iter < m.ntree; iter++) {
+    int changed = 0;
+    LANE_LOOP(ci, ncon) {
+      if (!wi[L.i_cact + ci]) continue;
+      int t1 = wi[L.i_ct1 + ci], t2 = wi[L.i_ct2 + ci];
+      if (t1 < 0 || t2 < 0 || t1 == t2) continue;
+      int a = ((volatile int*)island)[t1], b = ((volatile int*)island)[t2];
+      if (a != b) { int mn = a < b ? a : b; atomicMin(island + t1, mn); atomicMin(island + t2, mn); changed = 1; }
     }
-    if (lane < n && first[mydof] > minE) first[mydof] = minE;
-    __syncwarp();
-  }
-  if (lane == 0)
-    for (int i = 0; i < nsr; i++) {
+    LANE_LOOP(i, nsr) {
       if (!wi[L.i_sract + i]) continue;
       int A = wi[L.i_srA + i], B = wi[L.i_srB + i];
-      if (B < 0 || !tcoupled[m.dof_treeindex[A]]) continue;
-      int hi = A > B ? A : B, lo = A > B ? B : A;
-      if (first[hi] > lo) first[hi] = lo;
+      if (B < 0) continue;
+      int t1 = m.dof_treeindex[A], t2 = m.dof_treeindex[B];
+      if (t1 == t2) continue;
+      int a = ((volatile int*)island)[t1], b = ((volatile int*)island)[t2];
+      if (a != b) { int mn = a < b ? a : b; atomicMin(island + t1, mn); atomicMin(island + t2, mn); changed = 1; }
     }
-  __syncwarp();
-  // ... and the zero fill of the part of each row below its own tree block
+    changed = __any_sync(FULL, changed);
+    __syncwarp();
+    if (!changed) break;
+  }
+  // zero fill of the part of each coupled row that lies in the other (lower-numbered) trees of its island
   LANE_LOOP(i, m.nv) {
-    int root = m.tree_dofadr[m.dof_treeindex[i]];
-    for (int j = first[i]; j < root; j++) H[HIDX(i, j)] = 0;
+    int t = m.dof_treeindex[i];
+    if (!tcoupled[t]) continue;
+    int isl = island[t];
+    for (int tt = isl; tt < t; tt++) {
+      if (island[tt] != isl || !tcoupled[tt]) continue;
+      int lo = m.tree_dofadr[tt], hi = lo + m.tree_dofnum[tt];
+      for (int j = lo; j < hi; j++) H[HIDX(i, j)] = 0;
+    }
   }
   __syncwarp();
   // ---- pass 2: warp-cooperative accumulation, one lane per dof of the contact
@@ -294,13 +303,12 @@ __device__ __noinline__ bool mass_block_solve(double* ws, double* x, double hdam
   return true;
 }
 
-// x := -H^-1 g.  Uncoupled trees: 8-lane groups (group_chol_solve).  Coupled trees: skyline right-looking Cholesky with the
-// whole warp (each lane owns rows lane, lane+32, ...).
-__device__ __noinline__ void cholesky_solve(double* ws, const int* wi, double* x, const double* g_, int lane) {
+// x := -H^-1 g.  Uncoupled trees: 8-lane groups (group_chol_solve).  Coupled trees: right-looking dense Cholesky per island with
+// the whole warp (each lane owns rows lane, lane+32, ... of the island's dof list).
+__device__ __noinline__ void cholesky_solve(double* ws, int* wi, double* x, const double* g_, int lane) {
   const DevModel& m = c_m; const Layout& L = c_L;
   double* H = ws + L.H;
-  const int *first = wi + L.i_first, *tcoupled = wi + L.i_tcoupled;
-  int nv = m.nv;
+  const int* tcoupled = wi + L.i_tcoupled;
   bool any_coupled = false;
   for (int t = 0; t < m.ntree; t++) any_coupled |= tcoupled[t] != 0;
   {
@@ -314,46 +322,57 @@ __device__ __noinline__ void cholesky_solve(double* ws, const int* wi, double* x
   }
   __syncwarp();
   if (!any_coupled) return;
-  for (int j = 0; j < nv; j++) {
-    if (!tcoupled[m.dof_treeindex[j]]) continue;
-    double d = H[HIDX(j, j)];
-    if (d < GE_MINVAL) d = GE_MINVAL;
-    double ljj = sqrt(d), inv = 1.0 / ljj;
-    __syncwarp();
-    for (int i = j + 1 + lane; i < nv; i += 32)
-      if (first[i] <= j) H[HIDX(i, j)] *= inv;
-    if (lane == 0) H[HIDX(j, j)] = ljj;
-    __syncwarp();
-    for (int i = j + 1 + lane; i < nv; i += 32) {
-      if (first[i] > j) continue;
-      double lij = H[HIDX(i, j)];
-      if (lij == 0.0) continue;
-      for (int k = j + 1; k <= i; k++)
-        if (first[k] <= j) H[HIDX(i, k)] -= lij * H[HIDX(k, j)];
+  // coupled trees: one dense Cholesky per island over the island's dof list (ascending), rows spread over the lanes
+  const int* island = wi + L.i_island;
+  int* idx = (int*)wi + L.i_first;  // (the row-envelope array of the skyline version; free here)
+  for (int rep = 0; rep < m.ntree; rep++) {
+    if (!tcoupled[rep] || island[rep] != rep) continue;
+    int n = 0;
+    for (int t = rep; t < m.ntree; t++) {
+      if (!tcoupled[t] || island[t] != rep) continue;
+      int lo = m.tree_dofadr[t], nt = m.tree_dofnum[t];
+      LANE_LOOP(k, nt) idx[n + k] = lo + k;
+      n += nt;
     }
     __syncwarp();
+    for (int jj = 0; jj < n; jj++) {
+      const int j = idx[jj];
+      double d = H[HIDX(j, j)];
+      if (d < GE_MINVAL) d = GE_MINVAL;
+      double ljj = sqrt(d), inv = 1.0 / ljj;
+      __syncwarp();
+      for (int ii = jj + 1 + lane; ii < n; ii += 32) H[HIDX(idx[ii], j)] *= inv;
+      if (lane == 0) H[HIDX(j, j)] = ljj;
+      __syncwarp();
+      for (int ii = jj + 1 + lane; ii < n; ii += 32) {
+        const int i = idx[ii];
+        double lij = H[HIDX(i, j)];
+        if (lij == 0.0) continue;
+        for (int kk = jj + 1; kk <= ii; kk++) { const int k = idx[kk]; H[HIDX(i, k)] -= lij * H[HIDX(k, j)]; }
+      }
+      __syncwarp();
+    }
+    LANE_LOOP(ii, n) x[idx[ii]] = g_[idx[ii]];
+    __syncwarp();
+    for (int jj = 0; jj < n; jj++) {  // L y = g, column oriented
+      const int j = idx[jj];
+      double yj = x[j] / H[HIDX(j, j)];
+      __syncwarp();
+      if (lane == 0) x[j] = yj;
+      for (int ii = jj + 1 + lane; ii < n; ii += 32) x[idx[ii]] -= H[HIDX(idx[ii], j)] * yj;
+      __syncwarp();
+    }
+    for (int ii = n - 1; ii >= 0; ii--) {  // L^T x = y, column oriented
+      const int i = idx[ii];
+      double xi = x[i] / H[HIDX(i, i)];
+      __syncwarp();
+      if (lane == 0) x[i] = xi;
+      for (int kk = lane; kk < ii; kk += 32) x[idx[kk]] -= H[HIDX(i, idx[kk])] * xi;
+      __syncwarp();
+    }
+    LANE_LOOP(ii, n) x[idx[ii]] = -x[idx[ii]];
+    __syncwarp();
   }
-  LANE_LOOP(i, nv) if (tcoupled[m.dof_treeindex[i]]) x[i] = g_[i];
-  __syncwarp();
-  for (int j = 0; j < nv; j++) {  // L y = g, column oriented
-    if (!tcoupled[m.dof_treeindex[j]]) continue;
-    double yj = x[j] / H[HIDX(j, j)];
-    __syncwarp();
-    if (lane == 0) x[j] = yj;
-    for (int i = j + 1 + lane; i < nv; i += 32)
-      if (first[i] <= j) x[i] -= H[HIDX(i, j)] * yj;
-    __syncwarp();
-  }
-  for (int i = nv - 1; i >= 0; i--) {  // L^T x = y, column oriented
-    if (!tcoupled[m.dof_treeindex[i]]) continue;
-    double xi = x[i] / H[HIDX(i, i)];
-    __syncwarp();
-    if (lane == 0) x[i] = xi;
-    for (int k = first[i] + lane; k < i; k += 32) x[k] -= H[HIDX(i, k)] * xi;
-    __syncwarp();
-  }
-  LANE_LOOP(i, nv) if (tcoupled[m.dof_treeindex[i]]) x[i] = -x[i];
-  __syncwarp();
 }
 
 }  // namespace ge

@@ -52,7 +52,7 @@ struct Layout {
   // --- aliases inside scratch: solver phase
   int H, Vb, Wb;
   // --- ints
-  int i_cb1, i_cb2, i_ct1, i_ct2, i_cdim, i_cpair, i_cact, i_srA, i_srB, i_srtype, i_sract, i_cand, i_first, i_tcoupled, i_tcount, i_tlist, i_misc;
+  int i_cb1, i_cb2, i_ct1, i_ct2, i_cdim, i_cpair, i_cact, i_srA, i_srB, i_srtype, i_sract, i_cand, i_first, i_tcoupled, i_tcount, i_tlist, i_island;
   int total_ints;
   int total_bytes;
   int maxcon, maxcand;          // capacity of the contact / candidate lists

@@ -1,5 +1,7 @@
 // libgrasp_engine.so — C-ABI (include/grasp_engine.h) + kernels of the batched grasp-simulation engine.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC (see __graft_entry__.build()).
+#include "ge_variant.h"  // must come first: renames the namespace and the C entry points of this build variant
+
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -21,13 +23,14 @@ static int fail(int code, const char* fmt, const char* a = "") { snprintf(g_err,
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(GE_ERR_CUDA, "CUDA error: %s", cudaGetErrorString(e_)); } while (0)
 
 extern "C" const char* ge_last_error(void) { return g_err; }
-extern "C" const char* ge_version(void) { return "grasp_engine 0.1 sm_100a fp64 warp-per-env"; }
+extern "C" const char* ge_version(void) { return GE_WS_IN_HBM ? "grasp_engine 0.2 sm_100a fp64 warp-per-env (workspace: HBM rows)" : "grasp_engine 0.2 sm_100a fp64 warp-per-env (workspace: shared memory)"; }
 
 // ------------------------------------------------------------------------------------------------ kernels
 // Sub-step kernel: one warp per environment.  Loads the env's state rows into its shared-memory slice, runs up to `nsub`
 // iterations of the reference control loop (PID -> mj_step) including movement / grasp-program transitions, writes back.
 // A CTA holds `blockDim.y` warps (= environments); they meet at one barrier per sub-step so that the warps of an SM walk the
 // (large) sub-step code roughly together and share instruction-cache lines.
+namespace ge {
 __global__ void __launch_bounds__(256) k_run(EnvArrays E, int n_env, int nsub, double base_x, double base_y, double base_z, int stage_sync) {
   extern __shared__ double smem[];
   const DevModel& m = c_m; const Layout& L = c_L;
@@ -39,7 +42,11 @@ __global__ void __launch_bounds__(256) k_run(EnvArrays E, int n_env, int nsub, d
   p.phase = valid ? E.prog_phase[env] : PH_NONE;
   bool busy = c.active || p.phase != PH_NONE;
   if (!__syncthreads_or(busy)) return;
-  double* ws = L.ws_global ? E.gws + (size_t)(valid ? env : 0) * (L.total_bytes / 8) : smem + (size_t)threadIdx.y * (L.total_bytes / 8);
+#if GE_WS_IN_HBM
+  double* ws = E.gws + (size_t)(valid ? env : 0) * (L.total_bytes / 8);
+#else
+  double* ws = smem + (size_t)threadIdx.y * (L.total_bytes / 8);
+#endif
   int* wi = (int*)(ws + L.total_doubles);
   int info[12];
   unsigned char reward = 0;
@@ -103,7 +110,11 @@ __global__ void __launch_bounds__(32) k_debug(EnvArrays E, int env, int field, d
   extern __shared__ double smem[];
   const DevModel& m = c_m; const Layout& L = c_L;
   int lane = threadIdx.x;
-  double* ws = L.ws_global ? E.gws + (size_t)env * (L.total_bytes / 8) : smem;
+#if GE_WS_IN_HBM
+  double* ws = E.gws + (size_t)env * (L.total_bytes / 8);
+#else
+  double* ws = smem;
+#endif
   int* wi = (int*)(ws + L.total_doubles);
   LANE_LOOP(i, m.nq) ws[L.qpos + i] = E.qpos[(size_t)env * m.nq + i];
   LANE_LOOP(i, m.nv) { ws[L.qvel + i] = E.qvel[(size_t)env * m.nv + i]; ws[L.qaccws + i] = E.qaccws[(size_t)env * m.nv + i]; }
@@ -235,6 +246,8 @@ __global__ void __launch_bounds__(32) k_body_xpos(EnvArrays E, int n_env, double
   LANE_LOOP(i, 3 * m.nbody) xpos[(size_t)env * 3 * m.nbody + i] = ws[L.xpos + i];
 }
 
+}  // namespace ge
+
 // ------------------------------------------------------------------------------------------------ host side
 struct BlobEntry { char name[32]; int32_t dtype, ndim; int64_t shape[4]; int64_t offset, nbytes; };
 
@@ -333,7 +346,7 @@ static void make_layout(const DevModel& m, Layout& L, const int* tree_dofnum_h, 
   auto takeI = [&](int n) { int r = io; io += n; return r; };
   L.i_cb1 = takeI(L.maxcon); L.i_cb2 = takeI(L.maxcon); L.i_ct1 = takeI(L.maxcon); L.i_ct2 = takeI(L.maxcon); L.i_cdim = takeI(L.maxcon); L.i_cpair = takeI(L.maxcon); L.i_cact = takeI(L.maxcon);
   L.i_srA = takeI(GE_MAXSR); L.i_srB = takeI(GE_MAXSR); L.i_srtype = takeI(GE_MAXSR); L.i_sract = takeI(GE_MAXSR);
-  L.i_cand = takeI(L.maxcand); L.i_first = takeI(nv); L.i_tcoupled = takeI(m.ntree); L.i_tcount = takeI(m.ntree); L.i_tlist = takeI(m.ntree * GE_TLIST); L.i_misc = takeI(8);
+  L.i_cand = takeI(L.maxcand); L.i_first = takeI(nv); L.i_tcoupled = takeI(m.ntree); L.i_tcount = takeI(m.ntree); L.i_tlist = takeI(m.ntree * GE_TLIST); L.i_island = takeI(m.ntree);
   L.total_ints = align_up(io, 4);
   L.total_bytes = L.total_doubles * 8 + L.total_ints * 4;
   L.ws_global = 0;
@@ -398,10 +411,14 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
     memcpy(h->base_pos, bp, 24);
   }
   make_layout(m, h->lay, (const int*)blob_find(B, "tree_dofnum", nullptr), (const int*)blob_find(B, "tree_simple", nullptr), m.ntree);
-  // workspace placement: shared memory when one env fits a CTA's 227 KB, else one row per env in HBM (L1/L2-cached); GE_WS_GLOBAL=1
-  // forces the HBM placement (used by the tests to cover that path with the small scene)
-  h->lay.ws_global = h->lay.total_bytes > 227 * 1024 ? 1 : 0;
-  if (const char* ev = getenv("GE_WS_GLOBAL")) if (atoi(ev) != 0) h->lay.ws_global = 1;
+  // workspace placement is a property of the build variant (ge_variant.h): shared memory when one env fits a CTA's 227 KB,
+  // else one row per env in HBM; the dispatcher retries with the HBM variant on GE_ERR_TOO_LARGE
+#if GE_WS_IN_HBM
+  h->lay.ws_global = 1;
+#else
+  h->lay.ws_global = 0;
+  if (h->lay.total_bytes > 227 * 1024) { cudaFree(h->dblob); delete h; return fail(GE_ERR_TOO_LARGE, "per-env workspace exceeds shared memory"); }
+#endif
   if (h->lay.fk_bytes > 227 * 1024) { cudaFree(h->dblob); delete h; return fail(GE_ERR_MODEL, "model too large: kinematics workspace exceeds shared memory"); }
   CK(cudaMemcpyToSymbol(c_m, &m, sizeof m));
   CK(cudaMemcpyToSymbol(c_L, &h->lay, sizeof(Layout)));
@@ -419,7 +436,7 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
     }
     h->wpb = best;
   }
-  h->stage_sync = 1;
+  h->stage_sync = h->lay.ws_global ? 0 : 1;  // lock-step CTAs pay off for the small scene only (equal work per env, code-fetch bound)
   if (const char* ev = getenv("GE_STAGE_SYNC")) h->stage_sync = atoi(ev) != 0;
   if (const char* ev = getenv("GE_WPB")) { int v = atoi(ev); if (v >= 1 && v <= 8 && (h->lay.ws_global || v * h->lay.total_bytes <= 227 * 1024)) h->wpb = v; }
   h->ws_smem = h->lay.ws_global ? 0 : (size_t)h->lay.total_bytes;
