@@ -315,6 +315,49 @@ def run_ours(args):
                  "roofline": {"bound": "tensor", "achieved": tf, "peak": pk, "unit": "TFLOP/s", "frac": tf / pk,
                               "note": "41.99 GFLOP per 200x200 image (SURVEY 8d); peak = " + ("measured sustained cuBLAS bf16" if peaks else "fallback")},
                  "kernels_per_batch": (qf.launches - l_q0) // max(args.qnet_reps, 1)}
+    # ---- scene B (the reference's default 40-object scene): extra object, not the headline.  Envs are reset by
+    # the reference rule, 500 untimed sub-steps let the objects fall and pile up, then `scene_b_steps` sub-steps are timed.
+    sbinfo = None
+    if args.scene_b_envs > 0:
+        from mujoco_rl_ur5_b200.batched_env import HOME, scene_b_reset_qpos
+        from mujoco_rl_ur5_b200.engine import BatchedEngine
+        from mujoco_rl_ur5_b200.model.scene import load_scene, load_scene_blob
+
+        nb = args.scene_b_envs
+        Ab, _ = load_scene("B")
+        engb = BatchedEngine(load_scene_blob("B"), nb, local)
+        engb.set_state(np.stack([scene_b_reset_qpos(Ab, 20000 + rank * nb + i) for i in range(nb)]))
+        tgt = np.tile(HOME + np.array([0.2, 0.1, -0.1, 0.1, 0.1, 0.3, -0.1]), (nb, 1))
+        engb.move_group("All", tgt, 1e-9, 499)
+        engb.run()
+        barrier()
+        b0, b1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        b0.record()
+        engb.move_group("All", tgt, 1e-9, args.scene_b_steps - 1)
+        engb.run()
+        b1.record()
+        barrier()
+        tb = torch.tensor([b0.elapsed_time(b1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        flagged = int((engb.status() != 0).sum().item())
+        sbinfo = {"workload": f"scene B UR5gripper_2_finger_many_objects.xml (40 free objects, condim 6, nv 248), {nb} envs/GPU, "
+                              f"{args.scene_b_steps} PID+physics sub-steps in the piled-up state (after 500 untimed sub-steps)",
+                  "value": world * nb * args.scene_b_steps / (float(tb[0]) * 1e-3), "unit": UNIT, "envs_per_gpu": nb,
+                  "ms": float(tb[0]), "workspace": "HBM rows (engine variant hbm)", "envs_flagged": flagged}
+        if rank == 0 and args.cpu_seconds > 0:
+            from oracle.oracle_py import OracleEnv  # cpu_baseline leg: the checker timed beside the product, never on its path
+
+            o = OracleEnv(load_scene_blob("B"))
+            o.reset(scene_b_reset_qpos(Ab, 20000))
+            o.move_group("All", tgt[0], 1e-9, 249)
+            t0 = time.time()
+            o.move_group("All", tgt[0], 1e-9, 79)
+            dtb = time.time() - t0
+            o.close()
+            sbinfo["cpu_baseline"] = {"value": 80 / dtb, "unit": UNIT, "cores": 1, "kind": "port",
+                                      "sample": "fp64 oracle, one env, 80 sub-steps after 250 sub-steps of settling"}
+        engb.close()
     status = eng.status()
     status_or = int(torch.bitwise_or(status[0], status.max()).item()) if N else 0
     n_flag = int((status != 0).sum().item())
@@ -345,7 +388,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step, "d2h_bytes_per_step": env.d2h_bytes_per_step,
                     "steps": args.e2e_steps, "note": "BatchedGraspEnv.step: pinned host actions -> pixel_2_world -> full grasp attempts -> RGB-D render -> host rewards"},
             "gpu_launches": int(l1 - l0), "substep_kernel_launches": int(s1 - s0),
-            "clocks": clocks, "env_status_flags": {"envs_flagged": n_flag, "or": status_or}, "qnet": qinfo,
+            "clocks": clocks, "env_status_flags": {"envs_flagged": n_flag, "or": status_or}, "qnet": qinfo, "scene_b": sbinfo,
         }
         print(json.dumps(out))
     if world > 1:
@@ -365,6 +408,8 @@ def main():
     ap.add_argument("--qnet-images", type=int, default=256, help="images for the Q-net forward leg (0 = skip)")
     ap.add_argument("--qnet-chunk", type=int, default=64)
     ap.add_argument("--qnet-reps", type=int, default=3)
+    ap.add_argument("--scene-b-envs", type=int, default=1024, help="environments of the 40-object scene for the scene_b leg (0 = skip)")
+    ap.add_argument("--scene-b-steps", type=int, default=100)
     ap.add_argument("--ref-step-seconds", type=float, default=3.0, help="--impl reference: wall-time budget per worker and step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -18,8 +18,12 @@ import tempfile
 def function_ranges(so, kernel):
     d = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-    txt = subprocess.run(["nvdisasm", os.path.join(d, cubin)], capture_output=True, text=True).stdout
+    txt = ""
+    for cubin in sorted(f for f in os.listdir(d) if f.endswith(".cubin")):  # one cubin per translation unit (engine variants)
+        t = subprocess.run(["nvdisasm", os.path.join(d, cubin)], capture_output=True, text=True).stdout
+        if any(l.startswith(".text.") and kernel in l for l in t.splitlines()):
+            txt = t
+            break
     ranges, on, name = [], False, "(kernel body)"
     for line in txt.splitlines():
         if line.startswith(".text."):
@@ -30,7 +34,7 @@ def function_ranges(so, kernel):
             continue
         if line.startswith("$"):
             name = line.strip().rstrip(":").split("$")[-1]
-            m = re.search(r"_ZN2ge\d+([A-Za-z_0-9]+?)E", name)
+            m = re.search(r"_ZN\d+ge(?:_smem|_hbm)?\d+([A-Za-z_0-9]+?)E", name)
             name = m.group(1) if m else name
             continue
         m = re.match(r"\s+/\*([0-9a-f]{4,})\*/", line)

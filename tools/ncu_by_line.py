@@ -17,8 +17,12 @@ import tempfile
 def line_table(so, kernel):
     d = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-    txt = subprocess.run(["nvdisasm", "-gi", os.path.join(d, cubin)], capture_output=True, text=True).stdout
+    txt = ""
+    for cubin in sorted(f for f in os.listdir(d) if f.endswith(".cubin")):  # one cubin per translation unit (engine variants)
+        t = subprocess.run(["nvdisasm", "-gi", os.path.join(d, cubin)], capture_output=True, text=True).stdout
+        if any(l.startswith(".text.") and kernel in l for l in t.splitlines()):
+            txt = t
+            break
     table, on, cur = {}, False, ("?", 0)
     for line in txt.splitlines():
         if line.startswith(".text."):
@@ -40,7 +44,7 @@ def main():
     rep, so = sys.argv[1], sys.argv[2]
     filt = sys.argv[3] if len(sys.argv) > 3 else ""
     topn = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-    table = line_table(so, "k_run")
+    table = line_table(so, os.environ.get("NCU_KERNEL", "k_run"))
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
