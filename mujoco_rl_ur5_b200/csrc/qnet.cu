@@ -66,7 +66,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 // shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B stored contiguously (128 B);
-// LBO = byte distance between the two 16-byte K-chunks of one MMA, SBO = byte distance between 8-row groups
+// LBO = byte distance between the two 16-byte K-chunks of one MMA, SBO = byte distance between 8-row groups (kept for reference;
+// the convolution uses the 128-byte-swizzled layout below)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3fff);
@@ -74,6 +75,18 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
   d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
   return d;                // base offset 0, lbo mode 0, layout type 0 = SWIZZLE_NONE
+}
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: one tile row = 128 contiguous bytes (64 bf16 along K) whose eight 16-byte
+// chunks are XOR-ed with (row % 8); 8 rows form a 1024-byte atom (SBO), the tile base is 1024-byte aligned.  A K-step of 16
+// elements advances the start address by 32 bytes inside the atom.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;            // leading byte offset: unused for swizzled K-major
+  d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;            // layout type SWIZZLE_128B
+  return d;
 }
 // instruction descriptor kind::f16: D = F32, A = B = BF16, both K-major, shape M x N (K = 16)
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
@@ -85,70 +98,93 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // grid (ceil(H*W/128), Cout/BLOCK_N, B), 128 threads.  One CTA = 128 output pixels x BLOCK_N output channels of one image.
 #define BM 128
 #define BK 64
-template <int BLOCK_N>
+// 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes = 0 writes zeros (convolution padding, rows past the image)
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Main loop: STAGES shared-memory stages filled by cp.async two k-steps ahead of the MMA that consumes them (so that the stage
+// being refilled was read by an MMA issued a full iteration earlier), one thread issues the tcgen05.mma group per k-step and
+// commits it onto the stage's mbarrier.
+template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(128) k_conv_tc(const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ bias,
                                                  float* __restrict__ y, float* __restrict__ stats, int H, int W, int Cin, int Cout, int ks) {
   constexpr int A_STAGE = BM * BK * 2, B_STAGE = BLOCK_N * BK * 2;  // bytes
+  constexpr int DIST = STAGES - 2;                                   // prefetch distance in k-steps
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA = smem;                     // 2 stages
-  uint8_t* sB = smem + 2 * A_STAGE;       // 2 stages
-  uint64_t* mbar = (uint64_t*)(smem + 2 * A_STAGE + 2 * B_STAGE);  // [0,1] stage free, [2] accumulator ready
-  uint32_t* tmem_slot = (uint32_t*)(mbar + 3);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE;
+  uint64_t* mbar = (uint64_t*)(smem + STAGES * (A_STAGE + B_STAGE));  // [0..STAGES) stage free, [STAGES] accumulator ready
+  uint32_t* tmem_slot = (uint32_t*)(mbar + STAGES + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HW = H * W, m0 = blockIdx.x * BM, n0 = blockIdx.y * BLOCK_N, b = blockIdx.z;
   const int pad = ks / 2, taps = ks * ks, kchunks = Cin / BK, nk = taps * kchunks;
-  if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_init(&mbar[2], 1); fence_barrier_init(); }
+  if (tid == 0) { for (int i = 0; i <= STAGES; i++) mbar_init(&mbar[i], 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc(tmem_slot, BLOCK_N);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tacc = *tmem_slot;
   constexpr uint32_t idesc = make_idesc(BM, BLOCK_N);
-  // this thread's A row (output pixel) and B row (output channel)
-  const int m = m0 + tid;
-  const bool mvalid = m < HW;
-  const int oh = mvalid ? m / W : 0, ow = mvalid ? m % W : 0;
+  // copy mapping: consecutive lanes take consecutive 16-byte chunks of the same row (pixel / output channel), so a warp-level
+  // cp.async reads 4 full 128-byte lines and writes 4 swizzled 128-byte smem rows (conflict-free); thread -> chunk tid % 8 of
+  // rows tid / 8 + 16 * i
+  const int chunk = tid & 7, rbase = tid >> 3;
   const bf16* xb = x + (size_t)b * HW * Cin;
-  uint32_t phase[2] = {0, 0};
+  int pix[8];  // (oh << 16) | ow of this thread's 8 A rows, -1 past the image
+#pragma unroll
+  for (int i = 0; i < 8; i++) { const int mm = m0 + rbase + 16 * i; pix[i] = mm < HW ? ((mm / W) << 16) | (mm % W) : -1; }
+  auto issue_loads = [&](int kn) {
+    const int sn = kn % STAGES, tap = kn / kchunks, c0 = (kn % kchunks) * BK;
+    const int dh = tap / ks - pad, dw = tap % ks - pad;
+    uint8_t* dstA = sA + sn * A_STAGE;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int row = rbase + 16 * i, ih = (pix[i] >> 16) + dh, iw = (pix[i] & 0xffff) + dw;
+      const bool ok = pix[i] >= 0 && ih >= 0 && ih < H && iw >= 0 && iw < W;
+      const bf16* src = ok ? xb + ((size_t)ih * W + iw) * Cin + c0 + chunk * 8 : xb;
+      cp_async16(dstA + row * 128 + ((chunk ^ (row & 7)) << 4), src, ok ? 16u : 0u);
+    }
+    uint8_t* dstB = sB + sn * B_STAGE;
+#pragma unroll
+    for (int i = 0; i < BLOCK_N / 16; i++) {
+      const int row = rbase + 16 * i;
+      cp_async16(dstB + row * 128 + ((chunk ^ (row & 7)) << 4), w + ((size_t)(n0 + row) * taps + tap) * Cin + c0 + chunk * 8, 16u);
+    }
+  };
+  for (int kn = 0; kn < DIST; kn++) { if (kn < nk) issue_loads(kn); cp_async_commit(); }
   for (int kb = 0; kb < nk; kb++) {
-    const int s = kb & 1, tap = kb / kchunks, c0 = (kb % kchunks) * BK;
-    if (kb >= 2) { mbar_wait(&mbar[s], phase[s]); phase[s] ^= 1; }  // the MMAs that read this stage two iterations ago are done
-    // ---- gather A: 64 input channels of the tap-shifted pixel (zero outside the image), 8 x 16 B -> chunk-major smem
-    {
-      const int ih = oh + tap / ks - pad, iw = ow + tap % ks - pad;
-      const bool ok = mvalid && ih >= 0 && ih < H && iw >= 0 && iw < W;
-      const uint4* src = (const uint4*)(xb + ((size_t)ih * W + iw) * Cin + c0);
-      uint4* dst = (uint4*)(sA + s * A_STAGE);
-#pragma unroll
-      for (int c = 0; c < 8; c++) dst[c * BM + tid] = ok ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+    const int s = kb % STAGES, kn = kb + DIST;
+    if (kn < nk) {
+      // the stage being refilled was last read by the MMAs of k-step kn - STAGES = kb - 2
+      if (kn >= STAGES) mbar_wait(&mbar[kn % STAGES], ((kn - STAGES) / STAGES) & 1);
+      issue_loads(kn);
     }
-    // ---- gather B: 64 K-values of BLOCK_N output channels
-    {
-      uint4* dst = (uint4*)(sB + s * B_STAGE);
-      for (int r = tid; r < BLOCK_N; r += 128) {
-        const uint4* src = (const uint4*)(w + ((size_t)(n0 + r) * taps + tap) * Cin + c0);
-#pragma unroll
-        for (int c = 0; c < 8; c++) dst[c * BLOCK_N + r] = __ldg(src + c);
-      }
-    }
-    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    cp_async_commit();
+    cp_async_wait<DIST>();  // this thread's copies of k-step kb have landed
+    fence_proxy_async();    // generic-proxy smem writes -> visible to the tensor core (async proxy)
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
       const uint32_t a_base = smem_u32(sA + s * A_STAGE), b_base = smem_u32(sB + s * B_STAGE);
 #pragma unroll
       for (int k = 0; k < BK / 16; k++) {  // UMMA_K = 16 bf16 = two 16-byte chunks
-        uint64_t adesc = make_smem_desc(a_base + k * 2 * (BM * 16), BM * 16, 128);
-        uint64_t bdesc = make_smem_desc(b_base + k * 2 * (BLOCK_N * 16), BLOCK_N * 16, 128);
+        uint64_t adesc = make_smem_desc_sw128(a_base + k * 32);
+        uint64_t bdesc = make_smem_desc_sw128(b_base + k * 32);
         umma_bf16(tacc, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
       }
-      umma_commit(&mbar[s]);                 // frees the stage when these MMAs have read it
-      if (kb == nk - 1) umma_commit(&mbar[2]);  // accumulator complete
+      umma_commit(&mbar[s]);                      // frees the stage when these MMAs have read it
+      if (kb == nk - 1) umma_commit(&mbar[STAGES]);  // accumulator complete
     }
   }
-  mbar_wait(&mbar[2], 0);
+  mbar_wait(&mbar[STAGES], 0);
   tc_fence_after();
   // ---- epilogue: TMEM -> registers -> global fp32 (+bias), per-channel batch-norm statistics
+  const int m = m0 + tid;  // epilogue: thread t of warp w holds accumulator row 32 w + t
+  const bool mvalid = m < HW;
   float* yrow = y + ((size_t)b * HW + m) * Cout + n0;
   for (int cb = 0; cb < BLOCK_N; cb += 32) {
     float v[32];
@@ -339,13 +375,14 @@ extern "C" int gq_conv_tc(const void* x, const void* w, const float* bias, float
   cudaStream_t st = (cudaStream_t)stream;
   int bn = (Cout % 128 == 0) ? 128 : 64;
   dim3 grid((H * W + BM - 1) / BM, Cout / bn, B);
-  size_t smem = 2 * (BM * BK * 2) + 2 * ((size_t)bn * BK * 2) + 64;
+  constexpr int ST = 4;  // shared-memory stages (prefetch distance 2 k-steps): 128 KB per CTA at BLOCK_N = 128, 96 KB at 64
+  size_t smem = (size_t)ST * (BM * BK * 2) + (size_t)ST * ((size_t)bn * BK * 2) + 8 * (ST + 1) + 16;
   if (bn == 128) {
-    QCK(cudaFuncSetAttribute(k_conv_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_conv_tc<128><<<grid, 128, smem, st>>>((const bf16*)x, (const bf16*)w, bias, y, stats ? partials : nullptr, H, W, Cin, Cout, ks);
+    QCK(cudaFuncSetAttribute(k_conv_tc<128, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_conv_tc<128, ST><<<grid, 128, smem, st>>>((const bf16*)x, (const bf16*)w, bias, y, stats ? partials : nullptr, H, W, Cin, Cout, ks);
   } else {
-    QCK(cudaFuncSetAttribute(k_conv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_conv_tc<64><<<grid, 128, smem, st>>>((const bf16*)x, (const bf16*)w, bias, y, stats ? partials : nullptr, H, W, Cin, Cout, ks);
+    QCK(cudaFuncSetAttribute(k_conv_tc<64, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_conv_tc<64, ST><<<grid, 128, smem, st>>>((const bf16*)x, (const bf16*)w, bias, y, stats ? partials : nullptr, H, W, Cin, Cout, ks);
   }
   if (stats) {
     if (!partials) { snprintf(q_err, sizeof q_err, "gq_conv_tc: stats requested without a partials buffer"); return -1; }
