@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/grasp_qnet.h"
 
@@ -103,26 +104,33 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// arrive on the mbarrier once all cp.async issued so far by this thread have landed (does not bump the expected count)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
-// Main loop: STAGES shared-memory stages filled by cp.async two k-steps ahead of the MMA that consumes them (so that the stage
-// being refilled was read by an MMA issued a full iteration earlier), one thread issues the tcgen05.mma group per k-step and
-// commits it onto the stage's mbarrier.
+// Warp-specialised main loop, 160 threads: warps 0-3 are producers (cp.async gathers into a ring of STAGES shared-memory stages,
+// each thread signalling the stage's "full" mbarrier when its copies have landed), one thread of warp 4 waits for "full", issues the
+// tcgen05.mma group of the k-step and commits it onto the stage's "empty" mbarrier.  No CTA-wide barrier inside the loop.
 template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(128) k_conv_tc(const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ bias,
+__global__ void __launch_bounds__(160) k_conv_tc(const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ bias,
                                                  float* __restrict__ y, float* __restrict__ stats, int H, int W, int Cin, int Cout, int ks) {
   constexpr int A_STAGE = BM * BK * 2, B_STAGE = BLOCK_N * BK * 2;  // bytes
-  constexpr int DIST = STAGES - 2;                                   // prefetch distance in k-steps
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE;
-  uint64_t* mbar = (uint64_t*)(smem + STAGES * (A_STAGE + B_STAGE));  // [0..STAGES) stage free, [STAGES] accumulator ready
-  uint32_t* tmem_slot = (uint32_t*)(mbar + STAGES + 1);
+  uint64_t* full = (uint64_t*)(smem + STAGES * (A_STAGE + B_STAGE));  // [STAGES] copies landed (128 producer arrivals)
+  uint64_t* empty = full + STAGES;                                    // [STAGES] MMAs that read the stage are done (1 commit)
+  uint64_t* accbar = empty + STAGES;                                  // accumulator complete
+  uint32_t* tmem_slot = (uint32_t*)(accbar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HW = H * W, m0 = blockIdx.x * BM, n0 = blockIdx.y * BLOCK_N, b = blockIdx.z;
   const int pad = ks / 2, taps = ks * ks, kchunks = Cin / BK, nk = taps * kchunks;
-  if (tid == 0) { for (int i = 0; i <= STAGES; i++) mbar_init(&mbar[i], 1); fence_barrier_init(); }
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
+    mbar_init(accbar, 1);
+    fence_barrier_init();
+  }
   if (warp == 0) tmem_alloc(tmem_slot, BLOCK_N);
   tc_fence_before();
   __syncthreads();
@@ -155,32 +163,32 @@ __global__ void __launch_bounds__(128) k_conv_tc(const bf16* __restrict__ x, con
       cp_async16(dstB + row * 128 + ((chunk ^ (row & 7)) << 4), w + ((size_t)(n0 + row) * taps + tap) * Cin + c0 + chunk * 8, 16u);
     }
   };
-  for (int kn = 0; kn < DIST; kn++) { if (kn < nk) issue_loads(kn); cp_async_commit(); }
-  for (int kb = 0; kb < nk; kb++) {
-    const int s = kb % STAGES, kn = kb + DIST;
-    if (kn < nk) {
-      // the stage being refilled was last read by the MMAs of k-step kn - STAGES = kb - 2
-      if (kn >= STAGES) mbar_wait(&mbar[kn % STAGES], ((kn - STAGES) / STAGES) & 1);
+  if (warp < 4) {
+    for (int kn = 0; kn < nk; kn++) {
+      const int sn = kn % STAGES;
+      if (kn >= STAGES) mbar_wait(&empty[sn], ((kn - STAGES) / STAGES) & 1);  // the MMAs of k-step kn - STAGES have read the stage
       issue_loads(kn);
+      cp_async_mbar_arrive(&full[sn]);
     }
-    cp_async_commit();
-    cp_async_wait<DIST>();  // this thread's copies of k-step kb have landed
-    fence_proxy_async();    // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    __syncthreads();
-    if (tid == 0) {
+  } else if (lane == 0) {
+    for (int kb = 0; kb < nk; kb++) {
+      const int s = kb % STAGES;
+      mbar_wait(&full[s], (kb / STAGES) & 1);
+      fence_proxy_async();  // generic-proxy (cp.async) smem writes -> visible to the tensor core (async proxy)
       tc_fence_after();
       const uint32_t a_base = smem_u32(sA + s * A_STAGE), b_base = smem_u32(sB + s * B_STAGE);
 #pragma unroll
-      for (int k = 0; k < BK / 16; k++) {  // UMMA_K = 16 bf16 = two 16-byte chunks
+      for (int k = 0; k < BK / 16; k++) {  // UMMA_K = 16 bf16 = 32 bytes inside the swizzle atom
         uint64_t adesc = make_smem_desc_sw128(a_base + k * 32);
         uint64_t bdesc = make_smem_desc_sw128(b_base + k * 32);
         umma_bf16(tacc, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
       }
-      umma_commit(&mbar[s]);                      // frees the stage when these MMAs have read it
-      if (kb == nk - 1) umma_commit(&mbar[STAGES]);  // accumulator complete
+      umma_commit(&empty[s]);
+      if (kb == nk - 1) umma_commit(accbar);
     }
   }
-  mbar_wait(&mbar[STAGES], 0);
+  if (warp < 4) {
+  mbar_wait(accbar, 0);
   tc_fence_after();
   // ---- epilogue: TMEM -> registers -> global fp32 (+bias), per-channel batch-norm statistics
   const int m = m0 + tid;  // epilogue: thread t of warp w holds accumulator row 32 w + t
@@ -208,6 +216,7 @@ __global__ void __launch_bounds__(128) k_conv_tc(const bf16* __restrict__ x, con
         if (lane == 0) { float* pp = stats + ((((size_t)b * gridDim.x + blockIdx.x) * 4 + warp) * Cout + n0 + cb + i) * 2; pp[0] = s1; pp[1] = s2; }
       }
     }
+  }
   }
   tc_fence_before();
   __syncthreads();
@@ -367,23 +376,31 @@ extern "C" int gq_obs_to_state(const unsigned char* rgb, const float* depth, flo
   QCK(cudaGetLastError());
   return 0;
 }
-extern "C" const char* gq_version(void) { return "grasp_qnet 0.1 sm_100a bf16 tcgen05"; }
+extern "C" const char* gq_version(void) { return "grasp_qnet 0.2 sm_100a bf16 tcgen05 (warp-specialised cp.async producers, SW128 K-major)"; }
 
 extern "C" int gq_conv_tc(const void* x, const void* w, const float* bias, float* y, float* stats, float* partials, int B, int H, int W, int Cin, int Cout, int ks,
                           void* stream) {
   if (!x || !w || !y || (ks != 1 && ks != 3) || Cin % 64 || Cout % 64) { snprintf(q_err, sizeof q_err, "gq_conv_tc: bad argument"); return -1; }
   cudaStream_t st = (cudaStream_t)stream;
+  // tile shape: 128 output pixels x 64 / 128 / 256 output channels (the widest that divides Cout), 3 shared-memory stages so that two
+  // CTAs share an SM at BLOCK_N <= 128 (r01 sweep, whole forward: BN<=128/ST4 179, BN<=128/ST3 214, BN<=256/ST4 206, BN<=256/ST3 217
+  // TFLOP/s).  GQ_BN=128 / GQ_ST=4 override (tuning).
+  static int env_bn = -1, env_st = -1;
+  if (env_bn < 0) { const char* e = getenv("GQ_BN"); env_bn = e ? atoi(e) : 0; e = getenv("GQ_ST"); env_st = e ? atoi(e) : 0; }
   int bn = (Cout % 128 == 0) ? 128 : 64;
+  if (env_bn != 128 && Cout % 256 == 0) bn = 256;
+  int nst = env_st == 4 ? 4 : 3;
   dim3 grid((H * W + BM - 1) / BM, Cout / bn, B);
-  constexpr int ST = 4;  // shared-memory stages (prefetch distance 2 k-steps): 128 KB per CTA at BLOCK_N = 128, 96 KB at 64
-  size_t smem = (size_t)ST * (BM * BK * 2) + (size_t)ST * ((size_t)bn * BK * 2) + 8 * (ST + 1) + 16;
-  if (bn == 128) {
-    QCK(cudaFuncSetAttribute(k_conv_tc<128, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_conv_tc<128, ST><<<grid, 128, smem, st>>>((const bf16*)x, (const bf16*)w, bias, y, stats ? partials : nullptr, H, W, Cin, Cout, ks);
-  } else {
-    QCK(cudaFuncSetAttribute(k_conv_tc<64, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_conv_tc<64, ST><<<grid, 128, smem, st>>>((const bf16*)x, (const bf16*)w, bias, y, stats ? partials : nullptr, H, W, Cin, Cout, ks);
-  }
+  size_t smem = (size_t)nst * (BM * BK * 2) + (size_t)nst * ((size_t)bn * BK * 2) + 8 * (2 * nst + 1) + 16;
+#define LAUNCH_CONV(BN_, ST_)                                                                                                      \
+  do {                                                                                                                             \
+    QCK(cudaFuncSetAttribute(k_conv_tc<BN_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                         \
+    k_conv_tc<BN_, ST_><<<grid, 160, smem, st>>>((const bf16*)x, (const bf16*)w, bias, y, stats ? partials : nullptr, H, W, Cin, Cout, ks); \
+  } while (0)
+  if (bn == 256) { if (nst == 3) LAUNCH_CONV(256, 3); else LAUNCH_CONV(256, 4); }
+  else if (bn == 128) { if (nst == 3) LAUNCH_CONV(128, 3); else LAUNCH_CONV(128, 4); }
+  else { if (nst == 3) LAUNCH_CONV(64, 3); else LAUNCH_CONV(64, 4); }
+#undef LAUNCH_CONV
   if (stats) {
     if (!partials) { snprintf(q_err, sizeof q_err, "gq_conv_tc: stats requested without a partials buffer"); return -1; }
     k_bn_reduce<<<(B * Cout + 127) / 128, 128, 0, st>>>(partials, stats, B, (int)grid.x * 4, Cout);
