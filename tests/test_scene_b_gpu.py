@@ -160,3 +160,22 @@ def test_hbm_workspace_path_matches_shared_memory_path(scene_a):
         res.append((q.cpu().numpy().copy(), v.cpu().numpy().copy()))
         eng.close()
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+
+
+def test_facade_opens_reference_default_scene():
+    """GraspEnv(file=<the reference's default MJCF>) = scene B behind the reference API: reset() (global numpy RNG, 1 s settle),
+    observation shapes, one step() with a pixel action"""
+    from mujoco_rl_ur5_b200.grasp_env import GraspEnv
+
+    np.random.seed(3)
+    env = GraspEnv(file="/UR5+gripper/UR5gripper_2_finger_many_objects.xml", quiet=True, show_obs=False)
+    assert env.scene == "B" and env.engine.size(9) == 1
+    obs = env.reset()
+    assert obs["rgb"].shape == (200, 200, 3) and obs["depth"].shape == (200, 200)
+    assert 0.7 < float(np.min(obs["depth"])) < 1.15
+    q = env.engine.get_state()[0][0].cpu().numpy()
+    z = q[10:288:7]
+    assert (z < 1.2).all() and (z > -0.1).all()  # every object has landed (table, or the floor next to it)
+    obs, reward, done, info = env.step([100 * 200 + 100, 2])
+    assert reward in (0, 1) and done is False
+    env.close()
