@@ -179,3 +179,35 @@ def test_facade_opens_reference_default_scene():
     obs, reward, done, info = env.step([100 * 200 + 100, 2])
     assert reward in (0, 1) and done is False
     env.close()
+
+
+def test_scene_b_grasp_attempt_parity(scene_b):
+    """a whole move_and_grasp attempt into the 40-object pile (~1900 sub-steps): reward bit-exact, all per-phase step counts equal,
+    arm joint angles within the north-star tolerance 1e-4.  Individual objects of a pile may end up displaced (measured: one object
+    by 2 cm, every other coordinate < 1e-6): contact dynamics between many bodies amplify rounding differences."""
+    from mujoco_rl_ur5_b200.engine import BatchedEngine
+
+    blob, A, _ = scene_b
+    o = _oracle(blob)
+    o.reset(reset_qpos_scene_b(A, 0))
+    o.move_group("All", HOME + np.array([0, 0, 0, 0, 0, 0, 0.001]), 1e-9, 499)
+    q, v = o.qpos.copy(), o.qvel.copy()
+    pos = q[8:288].reshape(40, 7)[:, :3]
+    on_table = (pos[:, 2] > 0.85) & (pos[:, 2] < 1.0)
+    k = int((np.linalg.norm(pos[:, :2] - np.array([0.0, -0.6]), axis=1) + (~on_table) * 10).argmin())
+    coords = np.array([pos[k, 0], pos[k, 1], pos[k, 2] + 0.02])
+    eng = BatchedEngine(blob, 1, 0)
+    eng.set_state(q[None], v[None])
+    eng.grasp(coords[None], np.array([1], dtype=np.int32), 0.91)
+    assert eng.run() == 0
+    _, _, reward, _ = eng.results()
+    info = eng.grasp_info().cpu().numpy()[0].tolist()
+    gq = eng.get_state()[0][0].cpu().numpy()
+    assert int(eng.status()[0]) == 0
+    eng.close()
+    o.reset(q, v)
+    r, oinfo = o.move_and_grasp(coords, 1, 0.91)
+    assert int(reward[0]) == r and info == oinfo, (int(reward[0]), r, info, oinfo)
+    assert np.abs(gq[:8] - o.qpos[:8]).max() < 1e-4
+    assert np.median(np.abs(gq - o.qpos)) < 1e-6
+    o.close()
