@@ -277,33 +277,64 @@ __global__ void k_maxpool(const bf16* __restrict__ x, bf16* __restrict__ y, int 
   *(__nv_bfloat162*)(y + p * C + 2 * c2) = __floats2bfloat162_rn(m0, m1);
 }
 // y = relu( (x - mean) * rstd * gamma + beta [+ identity] ), per-image statistics from `stats` (sum, sumsq over H*W); fp32 in, bf16 out
-__global__ void k_bn_act(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
-                         const float* __restrict__ identity, bf16* __restrict__ y, int B, int HW, int C, float eps) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)B * HW * C;
-  if (i >= n) return;
-  int c = i % C, b = i / ((size_t)HW * C);
-  float s1 = stats[((size_t)b * C + c) * 2], s2 = stats[((size_t)b * C + c) * 2 + 1];
-  float mean = s1 / HW, var = fmaxf(s2 / HW - mean * mean, 0.f);  // biased variance, as BatchNorm uses for normalisation
-  float v = (x[i] - mean) * rsqrtf(var + eps) * gamma[c] + beta[c];
-  if (identity) v += identity[i];
-  y[i] = __float2bfloat16(fmaxf(v, 0.f));
+// one CTA = a run of pixels of one image: per-channel scale / shift (training-mode BatchNorm with the image's own statistics) are
+// prepared once in shared memory, then every thread streams 8 channels at a time (2 x 16 B in, 16 B out)
+__global__ void __launch_bounds__(256) k_bn_act(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                const float* __restrict__ beta, const float* __restrict__ identity, bf16* __restrict__ y, int HW, int C,
+                                                float eps, int pix_per_cta) {
+  extern __shared__ float sc[];  // scale[C], shift[C]
+  const int b = blockIdx.y, tid = threadIdx.x;
+  for (int c = tid; c < C; c += blockDim.x) {
+    float s1 = stats[((size_t)b * C + c) * 2], s2 = stats[((size_t)b * C + c) * 2 + 1];
+    float mean = s1 / HW, var = fmaxf(s2 / HW - mean * mean, 0.f);  // biased variance, as BatchNorm uses for normalisation
+    float scale = rsqrtf(var + eps) * gamma[c];
+    sc[c] = scale; sc[C + c] = beta[c] - mean * scale;
+  }
+  __syncthreads();
+  const int vc = C / 8, p0 = blockIdx.x * pix_per_cta, np = min(HW, p0 + pix_per_cta) - p0;
+  const size_t base = ((size_t)b * HW + p0) * C;
+  for (int i = tid; i < np * vc; i += blockDim.x) {
+    const int cv = (i % vc) * 8;
+    const size_t off = base + (size_t)(i / vc) * C + cv;
+    float v[8];
+    *(float4*)v = __ldg((const float4*)(x + off)); *(float4*)(v + 4) = __ldg((const float4*)(x + off + 4));
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = v[k] * sc[cv + k] + sc[C + cv + k];
+    if (identity) {
+      float r[8];
+      *(float4*)r = __ldg((const float4*)(identity + off)); *(float4*)(r + 4) = __ldg((const float4*)(identity + off + 4));
+#pragma unroll
+      for (int k = 0; k < 8; k++) v[k] += r[k];
+    }
+    __nv_bfloat162 o[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) o[k] = __floats2bfloat162_rn(fmaxf(v[2 * k], 0.f), fmaxf(v[2 * k + 1], 0.f));
+    *(uint4*)(y + off) = *(uint4*)o;
+  }
 }
-// nn.UpsamplingBilinear2d(scale_factor=2) = bilinear, align_corners=True; NHWC bf16
+// nn.UpsamplingBilinear2d(scale_factor=2) = bilinear, align_corners=True; NHWC bf16, 8 channels (16 B) per thread
 __global__ void k_upsample2x(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int H, int W, int C) {
-  int OH = 2 * H, OW = 2 * W;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)B * OH * OW * (C / 2);
+  int OH = 2 * H, OW = 2 * W, vc = C / 8;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)B * OH * OW * vc;
   if (i >= n) return;
-  int c2 = i % (C / 2);
-  size_t p = i / (C / 2);
+  int cv = (i % vc) * 8;
+  size_t p = i / vc;
   int ow = p % OW, oh = (p / OW) % OH, b = p / ((size_t)OW * OH);
   float fy = oh * (float)(H - 1) / (float)(OH - 1), fx = ow * (float)(W - 1) / (float)(OW - 1);
   int y0 = (int)fy, x0 = (int)fx, y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
   float wy = fy - y0, wx = fx - x0;
-  auto at = [&](int yy, int xx) { return __bfloat1622float2(*(const __nv_bfloat162*)(x + (((size_t)b * H + yy) * W + xx) * C + 2 * c2)); };
-  float2 a = at(y0, x0), bb = at(y0, x1), cc = at(y1, x0), d = at(y1, x1);
-  float r0 = (a.x * (1 - wx) + bb.x * wx) * (1 - wy) + (cc.x * (1 - wx) + d.x * wx) * wy;
-  float r1 = (a.y * (1 - wx) + bb.y * wx) * (1 - wy) + (cc.y * (1 - wx) + d.y * wx) * wy;
-  *(__nv_bfloat162*)(y + p * C + 2 * c2) = __floats2bfloat162_rn(r0, r1);
+  auto at = [&](int yy, int xx) { return __ldg((const uint4*)(x + (((size_t)b * H + yy) * W + xx) * C + cv)); };
+  uint4 qa = at(y0, x0), qb = at(y0, x1), qc = at(y1, x0), qd = at(y1, x1);
+  const __nv_bfloat162 *pa = (const __nv_bfloat162*)&qa, *pb = (const __nv_bfloat162*)&qb, *pc = (const __nv_bfloat162*)&qc, *pd = (const __nv_bfloat162*)&qd;
+  __nv_bfloat162 o[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    float2 a = __bfloat1622float2(pa[k]), bb = __bfloat1622float2(pb[k]), cc = __bfloat1622float2(pc[k]), d = __bfloat1622float2(pd[k]);
+    float r0 = (a.x * (1 - wx) + bb.x * wx) * (1 - wy) + (cc.x * (1 - wx) + d.x * wx) * wy;
+    float r1 = (a.y * (1 - wx) + bb.y * wx) * (1 - wy) + (cc.y * (1 - wx) + d.y * wx) * wy;
+    o[k] = __floats2bfloat162_rn(r0, r1);
+  }
+  *(uint4*)(y + p * C + cv) = *(uint4*)o;
 }
 // last layer: conv1x1 64 -> A (+bias) and sigmoid; x [B,HW,64] bf16, w [A][64] f32 -> q [B,A,HW] f32 (NCHW like the reference output)
 __global__ void k_head(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ q, int B, int HW, int A) {
@@ -421,13 +452,19 @@ extern "C" int gq_maxpool(const void* x, void* y, int B, int H, int W, int C, vo
 }
 extern "C" int gq_bn_act(const float* x, const float* stats, const float* gamma, const float* beta, const float* identity, void* y, int B, int HW, int C,
                          float eps, void* stream) {
-  size_t n = (size_t)B * HW * C;
-  k_bn_act<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, stats, gamma, beta, identity, (bf16*)y, B, HW, C, eps);
+  if (C % 8) { snprintf(q_err, sizeof q_err, "gq_bn_act: C must be a multiple of 8"); return -1; }
+  // enough CTAs per image to fill the GPU (148 SMs x 8) without making the per-CTA prologue (2 C floats) matter
+  int ctas = (148 * 8 + B - 1) / B;
+  int ppc = (HW + ctas - 1) / ctas;
+  if (ppc < 16) ppc = 16;
+  dim3 grid((HW + ppc - 1) / ppc, B);
+  k_bn_act<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(x, stats, gamma, beta, identity, (bf16*)y, HW, C, eps, ppc);
   QCK(cudaGetLastError());
   return 0;
 }
 extern "C" int gq_upsample2x(const void* x, void* y, int B, int H, int W, int C, void* stream) {
-  size_t n = (size_t)B * 4 * H * W * (C / 2);
+  if (C % 8) { snprintf(q_err, sizeof q_err, "gq_upsample2x: C must be a multiple of 8"); return -1; }
+  size_t n = (size_t)B * 4 * H * W * (C / 8);
   k_upsample2x<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, B, H, W, C);
   QCK(cudaGetLastError());
   return 0;
