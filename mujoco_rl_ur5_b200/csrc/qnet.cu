@@ -237,7 +237,7 @@ __global__ void k_bn_reduce(const float* __restrict__ part, float* __restrict__ 
 // ------------------------------------------------------------------------------------------------ small layers
 // first conv: x [B,4,H,W] f32 (NCHW, the agent's tensor), w [64][3][3][4] f32 -> y [B,H,W,64] bf16; no BN / ReLU follows (Modules.py:176)
 __global__ void k_conv_first(const float* __restrict__ x, const float* __restrict__ w, bf16* __restrict__ y, int B, int H, int W) {
-  __shared__ float sw[64 * 36];
+  __shared__ __align__(16) float sw[64 * 36];
   for (int i = threadIdx.x; i < 64 * 36; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
   int p = blockIdx.x * blockDim.x + threadIdx.x, HW = H * W;
@@ -252,29 +252,46 @@ __global__ void k_conv_first(const float* __restrict__ x, const float* __restric
     for (int c = 0; c < 4; c++) in[t * 4 + c] = ok ? x[((size_t)(b * 4 + c) * H + ih) * W + iw] : 0.f;
   }
   bf16* out = y + (size_t)p * 64;
-  for (int co = 0; co < 64; co += 2) {
-    float a0 = 0, a1 = 0;
+  const float4* sw4 = (const float4*)sw;  // 9 x 16-byte broadcast reads per output channel instead of 36 scalar ones
+  for (int co = 0; co < 64; co += 8) {
+    __nv_bfloat162 o[4];
 #pragma unroll
-    for (int k = 0; k < 36; k++) { a0 += in[k] * sw[co * 36 + k]; a1 += in[k] * sw[(co + 1) * 36 + k]; }
-    *(__nv_bfloat162*)(out + co) = __floats2bfloat162_rn(a0, a1);
+    for (int h = 0; h < 4; h++) {
+      float a0 = 0, a1 = 0;
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        float4 w0 = sw4[(co + 2 * h) * 9 + k], w1 = sw4[(co + 2 * h + 1) * 9 + k];
+        a0 += in[4 * k] * w0.x; a0 += in[4 * k + 1] * w0.y; a0 += in[4 * k + 2] * w0.z; a0 += in[4 * k + 3] * w0.w;
+        a1 += in[4 * k] * w1.x; a1 += in[4 * k + 1] * w1.y; a1 += in[4 * k + 2] * w1.z; a1 += in[4 * k + 3] * w1.w;
+      }
+      o[h] = __floats2bfloat162_rn(a0, a1);
+    }
+    *(uint4*)(out + co) = *(uint4*)o;
   }
 }
 // MaxPool2d(kernel 3, stride 2, padding 1) on NHWC bf16
 __global__ void k_maxpool(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int H, int W, int C) {
-  int OH = (H + 1) / 2, OW = (W + 1) / 2;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)B * OH * OW * (C / 2);
+  int OH = (H + 1) / 2, OW = (W + 1) / 2, vc = C / 8;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)B * OH * OW * vc;
   if (i >= n) return;
-  int c2 = i % (C / 2);
-  size_t p = i / (C / 2);
+  int cv = (i % vc) * 8;
+  size_t p = i / vc;
   int ow = p % OW, oh = (p / OW) % OH, b = p / ((size_t)OW * OH);
-  float m0 = -3.0e38f, m1 = -3.0e38f;
+  float m[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) m[k] = -3.0e38f;
   for (int dh = -1; dh <= 1; dh++) for (int dw = -1; dw <= 1; dw++) {
     int ih = 2 * oh + dh, iw = 2 * ow + dw;
     if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
-    float2 v = __bfloat1622float2(*(const __nv_bfloat162*)(x + (((size_t)b * H + ih) * W + iw) * C + 2 * c2));
-    m0 = fmaxf(m0, v.x); m1 = fmaxf(m1, v.y);
+    uint4 qv = __ldg((const uint4*)(x + (((size_t)b * H + ih) * W + iw) * C + cv));
+    const __nv_bfloat162* pv = (const __nv_bfloat162*)&qv;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { float2 v = __bfloat1622float2(pv[k]); m[2 * k] = fmaxf(m[2 * k], v.x); m[2 * k + 1] = fmaxf(m[2 * k + 1], v.y); }
   }
-  *(__nv_bfloat162*)(y + p * C + 2 * c2) = __floats2bfloat162_rn(m0, m1);
+  __nv_bfloat162 o[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) o[k] = __floats2bfloat162_rn(m[2 * k], m[2 * k + 1]);
+  *(uint4*)(y + p * C + cv) = *(uint4*)o;
 }
 // y = relu( (x - mean) * rstd * gamma + beta [+ identity] ), per-image statistics from `stats` (sum, sumsq over H*W); fp32 in, bf16 out
 // one CTA = a run of pixels of one image: per-channel scale / shift (training-mode BatchNorm with the image's own statistics) are
@@ -338,7 +355,7 @@ __global__ void k_upsample2x(const bf16* __restrict__ x, bf16* __restrict__ y, i
 }
 // last layer: conv1x1 64 -> A (+bias) and sigmoid; x [B,HW,64] bf16, w [A][64] f32 -> q [B,A,HW] f32 (NCHW like the reference output)
 __global__ void k_head(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ q, int B, int HW, int A) {
-  __shared__ float sw[8 * 64 + 8];
+  __shared__ __align__(16) float sw[8 * 64 + 8];
   for (int i = threadIdx.x; i < A * 64; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < A) sw[8 * 64 + threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
@@ -352,20 +369,31 @@ __global__ void k_head(const bf16* __restrict__ x, const float* __restrict__ w, 
   for (int a = 0; a < A; a++) {
     float acc = sw[8 * 64 + a];
 #pragma unroll
-    for (int c = 0; c < 64; c++) acc += in[c] * sw[a * 64 + c];
+    for (int c = 0; c < 16; c++) {
+      float4 wv = ((const float4*)sw)[a * 16 + c];
+      acc += in[4 * c] * wv.x; acc += in[4 * c + 1] * wv.y; acc += in[4 * c + 2] * wv.z; acc += in[4 * c + 3] * wv.w;
+    }
     q[((size_t)b * A + a) * HW + pix] = 1.f / (1.f + __expf(-acc));
   }
 }
 // flat arg-max over the A*HW Q-values of every image (Grasping_Agent_multidiscrete.py:295-299): idx = rot*HW + y*W + x
-__global__ void k_argmax(const float* __restrict__ q, int n, int* __restrict__ idx, float* __restrict__ val) {
-  __shared__ float sv[256];
-  __shared__ int si[256];
+__global__ void __launch_bounds__(1024) k_argmax(const float* __restrict__ q, int n, int* __restrict__ idx, float* __restrict__ val) {
+  __shared__ float sv[1024];
+  __shared__ int si[1024];
   const float* qb = q + (size_t)blockIdx.x * n;
-  float bv = -1.f; int bi = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) { float v = qb[i]; if (v > bv) { bv = v; bi = i; } }
+  float bv = -1.f; int bi = 0;  // Q-values are sigmoids (> 0); ties go to the lowest flat index, like torch.max over the flattened map
+  const int n4 = ((size_t)qb % 16 == 0) ? n / 4 : 0;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    float4 v = __ldg((const float4*)qb + i);
+    if (v.x > bv) { bv = v.x; bi = 4 * i; }
+    if (v.y > bv) { bv = v.y; bi = 4 * i + 1; }
+    if (v.z > bv) { bv = v.z; bi = 4 * i + 2; }
+    if (v.w > bv) { bv = v.w; bi = 4 * i + 3; }
+  }
+  for (int i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) { float v = qb[i]; if (v > bv) { bv = v; bi = i; } }
   sv[threadIdx.x] = bv; si[threadIdx.x] = bi;
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
+  for (int o = 512; o > 0; o >>= 1) {
     if (threadIdx.x < o) { float ov = sv[threadIdx.x + o]; int oi = si[threadIdx.x + o]; if (ov > sv[threadIdx.x] || (ov == sv[threadIdx.x] && oi < si[threadIdx.x])) { sv[threadIdx.x] = ov; si[threadIdx.x] = oi; } }
     __syncthreads();
   }
@@ -445,7 +473,7 @@ extern "C" int gq_conv_first(const float* x, const float* w, void* y, int B, int
   return 0;
 }
 extern "C" int gq_maxpool(const void* x, void* y, int B, int H, int W, int C, void* stream) {
-  size_t n = (size_t)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 2);
+  size_t n = (size_t)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
   k_maxpool<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, B, H, W, C);
   QCK(cudaGetLastError());
   return 0;
@@ -476,7 +504,7 @@ extern "C" int gq_head(const void* x, const float* w, const float* bias, float* 
   return 0;
 }
 extern "C" int gq_argmax(const float* q, int B, int n, int* idx, float* val, void* stream) {
-  k_argmax<<<B, 256, 0, (cudaStream_t)stream>>>(q, n, idx, val);
+  k_argmax<<<B, 1024, 0, (cudaStream_t)stream>>>(q, n, idx, val);
   QCK(cudaGetLastError());
   return 0;
 }
