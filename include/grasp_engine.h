@@ -7,6 +7,10 @@
  * device pointer owned by the caller (e.g. torch tensor storage); [host] pointers are ordinary host memory.
  * One handle per device; a handle is not thread-safe; launches go to the stream given at creation time
  * (0 = the legacy default stream).  N = number of environments of the handle.
+ *
+ * The library holds two builds of the engine (per-env workspace in shared memory / in HBM rows); ge_create picks one from the
+ * scene's size (ge_size(h, 9) tells which), every other entry point forwards through the handle.  Handles of different scenes may
+ * coexist in one process.
  */
 #ifndef GRASP_ENGINE_H
 #define GRASP_ENGINE_H
