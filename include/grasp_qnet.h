@@ -22,6 +22,12 @@ const char* gq_version(void);
  * deterministically through `partials`, a scratch buffer of B * ceil(H*W/128) * 4 * Cout * 2 floats. */
 int gq_conv_tc(const void* x, const void* w, const float* bias, float* y, float* stats, float* partials, int B, int H, int W, int Cin, int Cout, int ks,
                void* stream);
+/* Tail of BasicBlock.forward (Modules.py:136-142: `out = bn2(conv2(out)); identity = conv3(x); out += identity; out = relu(out)`) with the
+ * shortcut convolution doing the rest in its epilogue: out = relu((resid - mean) * rsqrt(var + eps) * gamma + beta + conv(x, w) + bias) as
+ * bf16 [B,H,W,Cout].  resid [B,H,W,Cout] f32 and stats [B,Cout,2] are conv2's outputs from gq_conv_tc; gamma / beta [Cout] are bn2's;
+ * scratch_scale_shift: B * Cout * 2 floats.  Same shapes and constraints as gq_conv_tc. */
+int gq_conv_tc_block_out(const void* x, const void* w, const float* bias, const float* resid, const float* stats, const float* gamma, const float* beta,
+                         float eps, float* scratch_scale_shift, void* out, int B, int H, int W, int Cin, int Cout, int ks, void* stream);
 /* Perception_Module.C1 = conv3x3(4, 64), no bias (Modules.py:163): x [B,4,H,W] f32 NCHW, w [64][3][3][4] f32, y [B,H,W,64] bf16 */
 int gq_conv_first(const float* x, const float* w, void* y, int B, int H, int W, void* stream);
 /* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) (Modules.py:164,166): x [B,H,W,C] -> y [B,ceil(H/2),ceil(W/2),C] */

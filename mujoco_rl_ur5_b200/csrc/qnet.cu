@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include "../../include/grasp_qnet.h"
+#include "qnet_plan.h"
 
 typedef __nv_bfloat16 bf16;
 
@@ -103,6 +104,25 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async16_s(uint32_t dst_smem_addr, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem_addr), "l"(src), "r"(src_bytes) : "memory");
+}
+// Column sums of a 32 x 32 tile held one row per lane (v[c] = element (lane, c)): on return lane j holds sum_lanes v[j].
+// Recursive halving: at distance s the lanes with bit s set keep the upper s columns of what they still hold and hand the lower s to
+// their partner (and vice versa), so 16 + 8 + 4 + 2 + 1 = 31 shuffles replace 32 x 5; the summation tree is fixed (deterministic).
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int k = 0; k < s; k++) {
+      const float send = up ? v[k] : v[k + s];
+      const float keep = up ? v[k + s] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 // arrive on the mbarrier once all cp.async issued so far by this thread have landed (does not bump the expected count)
 __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
@@ -112,8 +132,9 @@ __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
 // Warp-specialised main loop, 160 threads: warps 0-3 are producers (cp.async gathers into a ring of STAGES shared-memory stages,
 // each thread signalling the stage's "full" mbarrier when its copies have landed), one thread of warp 4 waits for "full", issues the
 // tcgen05.mma group of the k-step and commits it onto the stage's "empty" mbarrier.  No CTA-wide barrier inside the loop.
+// (first version, kept selectable with GQ_KERNEL=1 for A/B runs: ~700 producer instructions per warp and k-step, profiles/r01h)
 template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(160) k_conv_tc(const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ bias,
+__global__ void __launch_bounds__(160) k_conv_tc_v1(const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ bias,
                                                  float* __restrict__ y, float* __restrict__ stats, int H, int W, int Cin, int Cout, int ks) {
   constexpr int A_STAGE = BM * BK * 2, B_STAGE = BLOCK_N * BK * 2;  // bytes
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -221,6 +242,160 @@ __global__ void __launch_bounds__(160) k_conv_tc(const bf16* __restrict__ x, con
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tacc, BLOCK_N);
+}
+
+
+// ---- second version of the convolution kernel (default).  Same tiling, shared-memory layout, barrier protocol and MMA issue as v1;
+// what changed is what the ncu capture of v1 showed to be the limit (profiles/r01h_conv_tc_ncu_summary.txt: tensor pipe 17-23 % active,
+// issue slots 30-44 % busy with 1.25 resident warps per scheduler = the four producer warps executing ~700 instructions per k-step):
+//  * producer address arithmetic is hoisted out of the k-loop: every thread's 8 A rows and BLOCK_N/16 B rows are an arithmetic
+//    progression in global memory (row stride 16 pixels / 16 output channels) and in shared memory (2048 B: 16 rows x 128 B, the
+//    128-byte swizzle term depends on row % 8 only and is therefore the same for all rows of a thread); the zero-padding test of
+//    each (row, tap) is a bit of a per-row mask computed once; tap / channel-chunk / stage / phase are running counters (no divisions)
+//  * the per-channel BatchNorm partial sums of a 32 x 32 accumulator block use a transposing reduction (31 shuffles instead of 160)
+//    and are stored as one coalesced 256-byte row per warp
+//  * EPI == 1 (BasicBlock tail): the 1x1 shortcut convolution adds the normalised main branch and applies ReLU in its epilogue,
+//    out = relu(resid * scale + shift + conv(x) + bias) as bf16, which removes the fp32 round trip of the shortcut and one
+//    BN-apply kernel per block (BasicBlock.forward, Modules.py:128-142)
+template <int BLOCK_N, int STAGES, int EPI>
+__global__ void __launch_bounds__(160) k_conv_tc(const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ bias,
+                                                 float* __restrict__ y, float* __restrict__ stats, const float* __restrict__ resid,
+                                                 const float2* __restrict__ scale_shift, bf16* __restrict__ out, int H, int W, int Cin, int Cout,
+                                                 int ks) {
+  constexpr int A_STAGE = BM * BK * 2, B_STAGE = BLOCK_N * BK * 2;  // bytes
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE;
+  uint64_t* full = (uint64_t*)(smem + STAGES * (A_STAGE + B_STAGE));  // [STAGES] copies landed (128 producer arrivals)
+  uint64_t* empty = full + STAGES;                                    // [STAGES] MMAs that read the stage are done (1 commit)
+  uint64_t* accbar = empty + STAGES;                                  // accumulator complete
+  uint32_t* tmem_slot = (uint32_t*)(accbar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HW = H * W, m0 = blockIdx.x * BM, n0 = blockIdx.y * BLOCK_N, b = blockIdx.z;
+  const int pad = ks / 2, taps = ks * ks, kchunks = Cin / BK, nk = taps * kchunks;
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
+    mbar_init(accbar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tacc = *tmem_slot;
+  constexpr uint32_t idesc = make_idesc(BM, BLOCK_N);
+  if (warp < 4) {
+    // ---- producers.  Thread -> 16-byte chunk tid % 8 of rows tid / 8 + 16 i (consecutive lanes take consecutive chunks of one
+    // row: a warp-level cp.async reads 4 full 128-byte lines and writes 4 swizzled, conflict-free shared-memory rows).  The plan
+    // (qnet_plan.h) holds the per-thread constants and the running tap / chunk / stage counters.
+    ConvPlan p;
+    conv_plan_init(p, tid, m0, n0, H, W, Cin, ks);
+    const uint32_t sA_u = smem_u32(sA) + p.dstoff, sB_u = smem_u32(sB) + p.dstoff;
+    const char* xb = (const char*)(x + (size_t)b * HW * Cin);
+    const char* wb = (const char*)w;
+    for (int kn = 0; kn < nk; kn++) {
+      if (p.round > 0) mbar_wait(&empty[p.sn], (uint32_t)(p.round - 1) & 1u);  // the MMAs of k-step kn - STAGES have read the stage
+      const uint32_t tbit = 1u << p.tap;
+      const char* ap = xb + conv_plan_a(p, W, Cin);
+      const uint32_t da = sA_u + (uint32_t)(p.sn * A_STAGE);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const bool ok = (p.vmask[i] & tbit) != 0;
+        cp_async16_s(da + i * 2048, ok ? (const void*)ap : (const void*)xb, ok ? 16u : 0u);
+        ap += p.a_stride;
+      }
+      const char* bp = wb + conv_plan_b(p, kn);
+      const uint32_t db = sB_u + (uint32_t)(p.sn * B_STAGE);
+#pragma unroll
+      for (int i = 0; i < BLOCK_N / 16; i++) {
+        cp_async16_s(db + i * 2048, bp, 16u);
+        bp += p.b_stride;
+      }
+      cp_async_mbar_arrive(&full[p.sn]);
+      conv_plan_next(p, STAGES, kchunks, pad);
+    }
+  } else if (lane == 0) {
+    int s = 0; uint32_t ph = 0;
+    for (int kb = 0; kb < nk; kb++) {
+      mbar_wait(&full[s], ph);
+      fence_proxy_async();  // generic-proxy (cp.async) smem writes -> visible to the tensor core (async proxy)
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(sA + s * A_STAGE), b_base = smem_u32(sB + s * B_STAGE);
+#pragma unroll
+      for (int k = 0; k < BK / 16; k++) {  // UMMA_K = 16 bf16 = 32 bytes inside the swizzle atom
+        uint64_t adesc = make_smem_desc_sw128(a_base + k * 32);
+        uint64_t bdesc = make_smem_desc_sw128(b_base + k * 32);
+        umma_bf16(tacc, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+      }
+      umma_commit(&empty[s]);
+      if (kb == nk - 1) umma_commit(accbar);
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
+    }
+  }
+  if (warp < 4) {
+    mbar_wait(accbar, 0);
+    tc_fence_after();
+    // ---- epilogue: thread t of warp w holds accumulator row 32 w + t
+    const int m = m0 + tid;
+    const bool mvalid = m < HW;
+    const size_t rowoff = ((size_t)b * HW + m) * Cout + n0;
+    for (int cb = 0; cb < BLOCK_N; cb += 32) {
+      float v[32];
+      tmem_ld32(tacc + ((uint32_t)(warp * 32) << 16) + cb, v);
+      if (bias) {
+        const float4* b4 = (const float4*)(bias + n0 + cb);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const float4 bv = __ldg(b4 + i); v[4 * i] += bv.x; v[4 * i + 1] += bv.y; v[4 * i + 2] += bv.z; v[4 * i + 3] += bv.w; }
+      }
+      if constexpr (EPI == 0) {
+        if (mvalid) {
+          float4* dst = (float4*)(y + rowoff + cb);
+#pragma unroll
+          for (int i = 0; i < 8; i++) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        if (stats) {
+          float q[32];
+#pragma unroll
+          for (int i = 0; i < 32; i++) { v[i] = mvalid ? v[i] : 0.f; q[i] = v[i] * v[i]; }
+          const float s1 = warp_colsum32(v, lane), s2 = warp_colsum32(q, lane);
+          // deterministic: every (CTA, warp) writes its own partial row, k_bn_reduce adds them in a fixed order
+          float2* pp = (float2*)(stats + ((((size_t)b * gridDim.x + blockIdx.x) * 4 + warp) * Cout + n0 + cb) * 2);
+          pp[lane] = make_float2(s1, s2);
+        }
+      } else {
+        if (mvalid) {
+          const float4* r4 = (const float4*)(resid + rowoff + cb);
+          const float4* ss4 = (const float4*)(scale_shift + (size_t)b * Cout + n0 + cb);  // (scale, shift) pairs
+          __nv_bfloat162 o[16];
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const float4 r = __ldg(r4 + i);
+            const float4 sa = __ldg(ss4 + 2 * i), sb = __ldg(ss4 + 2 * i + 1);  // columns 4i, 4i+1 | 4i+2, 4i+3
+            const float o0 = fmaxf(r.x * sa.x + sa.y + v[4 * i], 0.f), o1 = fmaxf(r.y * sa.z + sa.w + v[4 * i + 1], 0.f);
+            const float o2 = fmaxf(r.z * sb.x + sb.y + v[4 * i + 2], 0.f), o3 = fmaxf(r.w * sb.z + sb.w + v[4 * i + 3], 0.f);
+            o[2 * i] = __floats2bfloat162_rn(o0, o1); o[2 * i + 1] = __floats2bfloat162_rn(o2, o3);
+          }
+          uint4* dst = (uint4*)(out + rowoff + cb);
+#pragma unroll
+          for (int i = 0; i < 4; i++) dst[i] = ((const uint4*)o)[i];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tacc, BLOCK_N);
+}
+// per-image BatchNorm (training mode, own statistics) folded into one multiply-add per channel: (scale, shift) from (sum, sum of squares)
+__global__ void k_bn_scale_shift(const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta, float2* __restrict__ ss,
+                                 int B, int C, int HW, float eps) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  int c = i % C;
+  float s1 = stats[(size_t)i * 2], s2 = stats[(size_t)i * 2 + 1];
+  float mean = s1 / HW, var = fmaxf(s2 / HW - mean * mean, 0.f);  // same expressions as k_bn_act
+  float scale = rsqrtf(var + eps) * gamma[c];
+  ss[i] = make_float2(scale, beta[c] - mean * scale);
 }
 
 // per-image batch-norm statistics from the per-(tile, warp) partials of k_conv_tc, summed in a fixed order (double accumulation)
@@ -435,35 +610,84 @@ extern "C" int gq_obs_to_state(const unsigned char* rgb, const float* depth, flo
   QCK(cudaGetLastError());
   return 0;
 }
-extern "C" const char* gq_version(void) { return "grasp_qnet 0.2 sm_100a bf16 tcgen05 (warp-specialised cp.async producers, SW128 K-major)"; }
+extern "C" const char* gq_version(void) { return "grasp_qnet 0.3 sm_100a bf16 tcgen05 (warp-specialised cp.async producers, SW128 K-major, fused block tail)"; }
+
+// tile shape: 128 output pixels x 64 / 128 / 256 output channels (the widest that divides Cout), 3 shared-memory stages so that two
+// CTAs share an SM at BLOCK_N <= 128 (r01 sweep with the v1 kernel, whole forward: BN<=128/ST4 179, BN<=128/ST3 214, BN<=256/ST4 206,
+// BN<=256/ST3 217 TFLOP/s).  Tuning overrides: GQ_BN=128, GQ_ST=4, GQ_KERNEL=1 (first kernel version).
+struct ConvCfg { int bn, nst, kernel; };
+static ConvCfg conv_cfg(int Cout) {
+  static int env_bn = -1, env_st = -1, env_k = -1;
+  if (env_bn < 0) {
+    const char* e = getenv("GQ_BN"); env_bn = e ? atoi(e) : 0;
+    e = getenv("GQ_ST"); env_st = e ? atoi(e) : 0;
+    e = getenv("GQ_KERNEL"); env_k = e ? atoi(e) : 2;
+  }
+  ConvCfg c;
+  c.bn = (Cout % 128 == 0) ? 128 : 64;
+  if (env_bn != 128 && Cout % 256 == 0) c.bn = 256;
+  c.nst = env_st == 4 ? 4 : 3;
+  c.kernel = env_k == 1 ? 1 : 2;
+  return c;
+}
+static size_t conv_smem(int bn, int nst) { return (size_t)nst * (BM * BK * 2) + (size_t)nst * ((size_t)bn * BK * 2) + 8 * (2 * nst + 1) + 16; }
+
+// EPI 0: y (+ BN partials); EPI 1: out = relu(resid * scale + shift + conv + bias) bf16
+template <int EPI>
+static int launch_conv(const ConvCfg& c, dim3 grid, cudaStream_t st, const bf16* x, const bf16* w, const float* bias, float* y, float* partials,
+                       const float* resid, const float2* ss, bf16* out, int H, int W, int Cin, int Cout, int ks) {
+  const size_t smem = conv_smem(c.bn, c.nst);
+#define LAUNCH_CONV(BN_, ST_)                                                                                                        \
+  do {                                                                                                                               \
+    QCK(cudaFuncSetAttribute(k_conv_tc<BN_, ST_, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
+    k_conv_tc<BN_, ST_, EPI><<<grid, 160, smem, st>>>(x, w, bias, y, partials, resid, ss, out, H, W, Cin, Cout, ks);                   \
+  } while (0)
+  if (c.bn == 256) { if (c.nst == 3) LAUNCH_CONV(256, 3); else LAUNCH_CONV(256, 4); }
+  else if (c.bn == 128) { if (c.nst == 3) LAUNCH_CONV(128, 3); else LAUNCH_CONV(128, 4); }
+  else { if (c.nst == 3) LAUNCH_CONV(64, 3); else LAUNCH_CONV(64, 4); }
+#undef LAUNCH_CONV
+  return 0;
+}
 
 extern "C" int gq_conv_tc(const void* x, const void* w, const float* bias, float* y, float* stats, float* partials, int B, int H, int W, int Cin, int Cout, int ks,
                           void* stream) {
   if (!x || !w || !y || (ks != 1 && ks != 3) || Cin % 64 || Cout % 64) { snprintf(q_err, sizeof q_err, "gq_conv_tc: bad argument"); return -1; }
+  if (stats && !partials) { snprintf(q_err, sizeof q_err, "gq_conv_tc: stats requested without a partials buffer"); return -1; }
   cudaStream_t st = (cudaStream_t)stream;
-  // tile shape: 128 output pixels x 64 / 128 / 256 output channels (the widest that divides Cout), 3 shared-memory stages so that two
-  // CTAs share an SM at BLOCK_N <= 128 (r01 sweep, whole forward: BN<=128/ST4 179, BN<=128/ST3 214, BN<=256/ST4 206, BN<=256/ST3 217
-  // TFLOP/s).  GQ_BN=128 / GQ_ST=4 override (tuning).
-  static int env_bn = -1, env_st = -1;
-  if (env_bn < 0) { const char* e = getenv("GQ_BN"); env_bn = e ? atoi(e) : 0; e = getenv("GQ_ST"); env_st = e ? atoi(e) : 0; }
-  int bn = (Cout % 128 == 0) ? 128 : 64;
-  if (env_bn != 128 && Cout % 256 == 0) bn = 256;
-  int nst = env_st == 4 ? 4 : 3;
-  dim3 grid((H * W + BM - 1) / BM, Cout / bn, B);
-  size_t smem = (size_t)nst * (BM * BK * 2) + (size_t)nst * ((size_t)bn * BK * 2) + 8 * (2 * nst + 1) + 16;
-#define LAUNCH_CONV(BN_, ST_)                                                                                                      \
-  do {                                                                                                                             \
-    QCK(cudaFuncSetAttribute(k_conv_tc<BN_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                         \
-    k_conv_tc<BN_, ST_><<<grid, 160, smem, st>>>((const bf16*)x, (const bf16*)w, bias, y, stats ? partials : nullptr, H, W, Cin, Cout, ks); \
+  const ConvCfg c = conv_cfg(Cout);
+  dim3 grid((H * W + BM - 1) / BM, Cout / c.bn, B);
+  if (c.kernel == 1) {
+    const size_t smem = conv_smem(c.bn, c.nst);
+#define LAUNCH_V1(BN_, ST_)                                                                                                          \
+  do {                                                                                                                               \
+    QCK(cudaFuncSetAttribute(k_conv_tc_v1<BN_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                        \
+    k_conv_tc_v1<BN_, ST_><<<grid, 160, smem, st>>>((const bf16*)x, (const bf16*)w, bias, y, stats ? partials : nullptr, H, W, Cin, Cout, ks); \
   } while (0)
-  if (bn == 256) { if (nst == 3) LAUNCH_CONV(256, 3); else LAUNCH_CONV(256, 4); }
-  else if (bn == 128) { if (nst == 3) LAUNCH_CONV(128, 3); else LAUNCH_CONV(128, 4); }
-  else { if (nst == 3) LAUNCH_CONV(64, 3); else LAUNCH_CONV(64, 4); }
-#undef LAUNCH_CONV
-  if (stats) {
-    if (!partials) { snprintf(q_err, sizeof q_err, "gq_conv_tc: stats requested without a partials buffer"); return -1; }
-    k_bn_reduce<<<(B * Cout + 127) / 128, 128, 0, st>>>(partials, stats, B, (int)grid.x * 4, Cout);
+    if (c.bn == 256) { if (c.nst == 3) LAUNCH_V1(256, 3); else LAUNCH_V1(256, 4); }
+    else if (c.bn == 128) { if (c.nst == 3) LAUNCH_V1(128, 3); else LAUNCH_V1(128, 4); }
+    else { if (c.nst == 3) LAUNCH_V1(64, 3); else LAUNCH_V1(64, 4); }
+#undef LAUNCH_V1
+  } else {
+    int r = launch_conv<0>(c, grid, st, (const bf16*)x, (const bf16*)w, bias, y, stats ? partials : nullptr, nullptr, nullptr, nullptr, H, W, Cin, Cout, ks);
+    if (r) return r;
   }
+  if (stats) k_bn_reduce<<<(B * Cout + 127) / 128, 128, 0, st>>>(partials, stats, B, (int)grid.x * 4, Cout);
+  QCK(cudaGetLastError());
+  return 0;
+}
+extern "C" int gq_conv_tc_block_out(const void* x, const void* w, const float* bias, const float* resid, const float* stats, const float* gamma,
+                                    const float* beta, float eps, float* scratch_scale_shift, void* out, int B, int H, int W, int Cin, int Cout, int ks,
+                                    void* stream) {
+  if (!x || !w || !resid || !stats || !gamma || !beta || !scratch_scale_shift || !out || (ks != 1 && ks != 3) || Cin % 64 || Cout % 64) {
+    snprintf(q_err, sizeof q_err, "gq_conv_tc_block_out: bad argument");
+    return -1;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const ConvCfg c = conv_cfg(Cout);
+  dim3 grid((H * W + BM - 1) / BM, Cout / c.bn, B);
+  k_bn_scale_shift<<<(B * Cout + 127) / 128, 128, 0, st>>>(stats, gamma, beta, (float2*)scratch_scale_shift, B, Cout, H * W, eps);
+  int r = launch_conv<1>(c, grid, st, (const bf16*)x, (const bf16*)w, bias, nullptr, nullptr, resid, (const float2*)scratch_scale_shift, (bf16*)out, H, W, Cin, Cout, ks);
+  if (r) return r;
   QCK(cudaGetLastError());
   return 0;
 }

@@ -20,7 +20,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 QLIB_PATH = os.path.join(_HERE, "csrc", "libgrasp_qnet.so")
 _QLIB = None
-QSYMBOLS = ["gq_last_error", "gq_version", "gq_conv_tc", "gq_conv_first", "gq_maxpool", "gq_bn_act", "gq_upsample2x", "gq_head", "gq_argmax", "gq_obs_to_state"]
+QSYMBOLS = ["gq_last_error", "gq_version", "gq_conv_tc", "gq_conv_tc_block_out", "gq_conv_first", "gq_maxpool", "gq_bn_act", "gq_upsample2x", "gq_head", "gq_argmax", "gq_obs_to_state"]
 
 
 def load_qnet_library():
@@ -33,6 +33,7 @@ def load_qnet_library():
         L.gq_last_error.restype = C.c_char_p
         L.gq_version.restype = C.c_char_p
         L.gq_conv_tc.argtypes = [P, P, P, P, P, P, I, I, I, I, I, I, P]
+        L.gq_conv_tc_block_out.argtypes = [P, P, P, P, P, P, P, F, P, P, I, I, I, I, I, I, P]
         L.gq_conv_first.argtypes = [P, P, P, I, I, I, P]
         L.gq_maxpool.argtypes = [P, P, I, I, I, I, P]
         L.gq_bn_act.argtypes = [P, P, P, P, P, P, I, I, I, F, P]
@@ -126,6 +127,8 @@ class QNetForward:
                      g2=sd[f"{name}.bn2.weight"].contiguous(), be2=sd[f"{name}.bn2.bias"].contiguous(),
                      cin=sd[f"{name}.conv1.weight"].shape[1], cout=sd[f"{name}.conv1.weight"].shape[0])
             self.blocks.append(b)
+        # BasicBlock tail: shortcut conv + BN-apply of the main branch + add + ReLU in one kernel (GQ_FUSE_TAIL=0: separate kernels)
+        self.fuse_tail = os.environ.get("GQ_FUSE_TAIL", "1") != "0"
         self.w_head = sd["1.C1.weight"].reshape(self.A, 64).contiguous()
         self.b_head = sd["1.C1.bias"].contiguous()
         self.launches = 0
@@ -150,6 +153,16 @@ class QNetForward:
         self._ck(self.L.gq_conv_tc(self._p(x), self._p(w), self._p(bias), self._p(y), self._p(stats), self._p(part), B, H, W, cin, cout, ks, self._stream()), "gq_conv_tc")
         return y, stats
 
+    def conv_tc_block_out(self, x, w, bias, resid, stats, gamma, beta, B, H, W, cin, cout, ks=1):
+        """relu(BN(resid; per-image stats, gamma, beta) + conv(x, w) + bias) -> bf16 [B, H*W, cout]: the tail of BasicBlock.forward
+        (Modules.py:136-142) with the shortcut convolution's epilogue doing the normalisation, the add and the ReLU"""
+        t = self.torch
+        y = t.empty((B, H * W, cout), dtype=t.bfloat16, device=self.dev)
+        ss = t.empty((B, cout, 2), dtype=t.float32, device=self.dev)
+        self._ck(self.L.gq_conv_tc_block_out(self._p(x), self._p(w), self._p(bias), self._p(resid), self._p(stats), self._p(gamma), self._p(beta), 1e-5,
+                                              self._p(ss), self._p(y), B, H, W, cin, cout, ks, self._stream()), "gq_conv_tc_block_out")
+        return y
+
     def bn_act(self, x, stats, gamma, beta, identity, B, HW, Cc):
         t = self.torch
         y = t.empty((B, HW, Cc), dtype=t.bfloat16, device=self.dev)
@@ -162,6 +175,8 @@ class QNetForward:
         o1, s1 = self.conv_tc(x, blk["w1"], None, B, H, W, cin, cout, 3, True)
         a1 = self.bn_act(o1, s1, blk["g1"], blk["be1"], None, B, H * W, cout)
         o2, s2 = self.conv_tc(a1, blk["w2"], None, B, H, W, cout, cout, 3, True)
+        if self.fuse_tail:
+            return self.conv_tc_block_out(x, blk["w3"], blk["b3"], o2, s2, blk["g2"], blk["be2"], B, H, W, cin, cout, 1)
         idn, _ = self.conv_tc(x, blk["w3"], blk["b3"], B, H, W, cin, cout, 1, False)
         return self.bn_act(o2, s2, blk["g2"], blk["be2"], idn, B, H * W, cout)
 

@@ -19,8 +19,10 @@ def build():
 def lib():
     global _LIB
     if _LIB is None:
-        so = os.path.join(_DIR, "libgrasp_oracle.so")
-        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(_DIR, "grasp_oracle.c")):
+        so = os.environ.get("GRASP_ORACLE_SO") or os.path.join(_DIR, "libgrasp_oracle.so")  # override: rounding-sensitivity experiments
+        if os.environ.get("GRASP_ORACLE_SO"):
+            pass
+        elif not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(_DIR, "grasp_oracle.c")):
             build()
         L = C.CDLL(so)
         P, D, I = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
