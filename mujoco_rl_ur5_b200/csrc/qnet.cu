@@ -107,6 +107,10 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint
 __device__ __forceinline__ void cp_async16_s(uint32_t dst_smem_addr, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem_addr), "l"(src), "r"(src_bytes) : "memory");
 }
+// .cg: cache in L2 only (weight tiles are read once per CTA; keeping them out of L1 leaves it to the activation rows the 9 taps re-read)
+__device__ __forceinline__ void cp_async16_cg(uint32_t dst_smem_addr, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem_addr), "l"(src) : "memory");
+}
 // Column sums of a 32 x 32 tile held one row per lane (v[c] = element (lane, c)): on return lane j holds sum_lanes v[j].
 // Recursive halving: at distance s the lanes with bit s set keep the upper s columns of what they still hold and hand the lower s to
 // their partner (and vice versa), so 16 + 8 + 4 + 2 + 1 = 31 shuffles replace 32 x 5; the summation tree is fixed (deterministic).
@@ -257,24 +261,27 @@ __global__ void __launch_bounds__(160) k_conv_tc_v1(const bf16* __restrict__ x, 
 //  * EPI == 1 (BasicBlock tail): the 1x1 shortcut convolution adds the normalised main branch and applies ReLU in its epilogue,
 //    out = relu(resid * scale + shift + conv(x) + bias) as bf16, which removes the fp32 round trip of the shortcut and one
 //    BN-apply kernel per block (BasicBlock.forward, Modules.py:128-142)
-template <int BLOCK_N, int STAGES, int EPI>
-__global__ void __launch_bounds__(160) k_conv_tc(const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ bias,
+//  * NPW = 4 or 8 producer warps (GQ_NPW): 8 halves the copies per thread and lets warps 4-7 take half of the epilogue columns (a warp
+//    may read the TMEM lane quarter warp % 4, so warps w and w + 4 share rows and split columns)
+template <int BLOCK_N, int STAGES, int EPI, int NPW>
+__global__ void __launch_bounds__(32 * (NPW + 1)) k_conv_tc(const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ bias,
                                                  float* __restrict__ y, float* __restrict__ stats, const float* __restrict__ resid,
                                                  const float2* __restrict__ scale_shift, bf16* __restrict__ out, int H, int W, int Cin, int Cout,
-                                                 int ks) {
+                                                 int ks, int cg_weights) {
   constexpr int A_STAGE = BM * BK * 2, B_STAGE = BLOCK_N * BK * 2;  // bytes
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE;
-  uint64_t* full = (uint64_t*)(smem + STAGES * (A_STAGE + B_STAGE));  // [STAGES] copies landed (128 producer arrivals)
+  uint64_t* full = (uint64_t*)(smem + STAGES * (A_STAGE + B_STAGE));  // [STAGES] copies landed (32 NPW producer arrivals)
   uint64_t* empty = full + STAGES;                                    // [STAGES] MMAs that read the stage are done (1 commit)
   uint64_t* accbar = empty + STAGES;                                  // accumulator complete
   uint32_t* tmem_slot = (uint32_t*)(accbar + 1);
+  constexpr int RS = 4 * NPW;  // row step of the copy mapping (qnet_plan.h): producer threads / 8
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HW = H * W, m0 = blockIdx.x * BM, n0 = blockIdx.y * BLOCK_N, b = blockIdx.z;
   const int pad = ks / 2, taps = ks * ks, kchunks = Cin / BK, nk = taps * kchunks;
   if (tid == 0) {
-    for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 32 * NPW); mbar_init(&empty[i], 1); }
     mbar_init(accbar, 1);
     fence_barrier_init();
   }
@@ -284,12 +291,12 @@ __global__ void __launch_bounds__(160) k_conv_tc(const bf16* __restrict__ x, con
   tc_fence_after();
   const uint32_t tacc = *tmem_slot;
   constexpr uint32_t idesc = make_idesc(BM, BLOCK_N);
-  if (warp < 4) {
-    // ---- producers.  Thread -> 16-byte chunk tid % 8 of rows tid / 8 + 16 i (consecutive lanes take consecutive chunks of one
+  if (warp < NPW) {
+    // ---- producers.  Thread -> 16-byte chunk tid % 8 of rows tid / 8 + RS i (consecutive lanes take consecutive chunks of one
     // row: a warp-level cp.async reads 4 full 128-byte lines and writes 4 swizzled, conflict-free shared-memory rows).  The plan
     // (qnet_plan.h) holds the per-thread constants and the running tap / chunk / stage counters.
     ConvPlan p;
-    conv_plan_init(p, tid, m0, n0, H, W, Cin, ks);
+    conv_plan_init<RS>(p, tid, m0, n0, H, W, Cin, ks);
     const uint32_t sA_u = smem_u32(sA) + p.dstoff, sB_u = smem_u32(sB) + p.dstoff;
     const char* xb = (const char*)(x + (size_t)b * HW * Cin);
     const char* wb = (const char*)w;
@@ -299,22 +306,22 @@ __global__ void __launch_bounds__(160) k_conv_tc(const bf16* __restrict__ x, con
       const char* ap = xb + conv_plan_a(p, W, Cin);
       const uint32_t da = sA_u + (uint32_t)(p.sn * A_STAGE);
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
+      for (int i = 0; i < BM / RS; i++) {
         const bool ok = (p.vmask[i] & tbit) != 0;
-        cp_async16_s(da + i * 2048, ok ? (const void*)ap : (const void*)xb, ok ? 16u : 0u);
+        cp_async16_s(da + i * (RS * 128), ok ? (const void*)ap : (const void*)xb, ok ? 16u : 0u);
         ap += p.a_stride;
       }
       const char* bp = wb + conv_plan_b(p, kn);
       const uint32_t db = sB_u + (uint32_t)(p.sn * B_STAGE);
 #pragma unroll
-      for (int i = 0; i < BLOCK_N / 16; i++) {
-        cp_async16_s(db + i * 2048, bp, 16u);
+      for (int i = 0; i < BLOCK_N / RS; i++) {
+        if (cg_weights) cp_async16_cg(db + i * (RS * 128), bp); else cp_async16_s(db + i * (RS * 128), bp, 16u);
         bp += p.b_stride;
       }
       cp_async_mbar_arrive(&full[p.sn]);
       conv_plan_next(p, STAGES, kchunks, pad);
     }
-  } else if (lane == 0) {
+  } else if (lane == 0) {  // warp NPW: the MMA issuer
     int s = 0; uint32_t ph = 0;
     for (int kb = 0; kb < nk; kb++) {
       mbar_wait(&full[s], ph);
@@ -332,16 +339,20 @@ __global__ void __launch_bounds__(160) k_conv_tc(const bf16* __restrict__ x, con
       if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
   }
-  if (warp < 4) {
+  if (warp < NPW) {
     mbar_wait(accbar, 0);
     tc_fence_after();
-    // ---- epilogue: thread t of warp w holds accumulator row 32 w + t
-    const int m = m0 + tid;
+    // ---- epilogue: lane t of a warp with warp % 4 == q holds accumulator row 32 q + t; with 8 warps, warps 4-7 take the upper half of
+    // the columns
+    const int quarter = warp & 3;
+    const int m = m0 + quarter * 32 + lane;
     const bool mvalid = m < HW;
     const size_t rowoff = ((size_t)b * HW + m) * Cout + n0;
-    for (int cb = 0; cb < BLOCK_N; cb += 32) {
+    constexpr int CB_PER_WARP = BLOCK_N / (NPW / 4);
+    const int cb0 = (warp >> 2) * CB_PER_WARP;
+    for (int cb = cb0; cb < cb0 + CB_PER_WARP; cb += 32) {
       float v[32];
-      tmem_ld32(tacc + ((uint32_t)(warp * 32) << 16) + cb, v);
+      tmem_ld32(tacc + ((uint32_t)(quarter * 32) << 16) + cb, v);
       if (bias) {
         const float4* b4 = (const float4*)(bias + n0 + cb);
 #pragma unroll
@@ -359,7 +370,7 @@ __global__ void __launch_bounds__(160) k_conv_tc(const bf16* __restrict__ x, con
           for (int i = 0; i < 32; i++) { v[i] = mvalid ? v[i] : 0.f; q[i] = v[i] * v[i]; }
           const float s1 = warp_colsum32(v, lane), s2 = warp_colsum32(q, lane);
           // deterministic: every (CTA, warp) writes its own partial row, k_bn_reduce adds them in a fixed order
-          float2* pp = (float2*)(stats + ((((size_t)b * gridDim.x + blockIdx.x) * 4 + warp) * Cout + n0 + cb) * 2);
+          float2* pp = (float2*)(stats + ((((size_t)b * gridDim.x + blockIdx.x) * 4 + quarter) * Cout + n0 + cb) * 2);
           pp[lane] = make_float2(s1, s2);
         }
       } else {
@@ -614,20 +625,23 @@ extern "C" const char* gq_version(void) { return "grasp_qnet 0.3 sm_100a bf16 tc
 
 // tile shape: 128 output pixels x 64 / 128 / 256 output channels (the widest that divides Cout), 3 shared-memory stages so that two
 // CTAs share an SM at BLOCK_N <= 128 (r01 sweep with the v1 kernel, whole forward: BN<=128/ST4 179, BN<=128/ST3 214, BN<=256/ST4 206,
-// BN<=256/ST3 217 TFLOP/s).  Tuning overrides: GQ_BN=128, GQ_ST=4, GQ_KERNEL=1 (first kernel version).
-struct ConvCfg { int bn, nst, kernel; };
+// BN<=256/ST3 217 TFLOP/s).  Tuning overrides: GQ_BN=128, GQ_ST=4, GQ_NPW=8 (producer warps), GQ_CGB=1 (weights bypass L1), GQ_KERNEL=1 (first kernel version).
+struct ConvCfg { int bn, nst, kernel, npw, cg; };
 static ConvCfg conv_cfg(int Cout) {
-  static int env_bn = -1, env_st = -1, env_k = -1;
+  static int env_bn = -1, env_st = -1, env_k = -1, env_npw = 4, env_cg = 0;
   if (env_bn < 0) {
     const char* e = getenv("GQ_BN"); env_bn = e ? atoi(e) : 0;
     e = getenv("GQ_ST"); env_st = e ? atoi(e) : 0;
     e = getenv("GQ_KERNEL"); env_k = e ? atoi(e) : 2;
+    e = getenv("GQ_NPW"); env_npw = (e && atoi(e) == 8) ? 8 : 4;
+    e = getenv("GQ_CGB"); env_cg = (e && atoi(e) != 0) ? 1 : 0;
   }
   ConvCfg c;
   c.bn = (Cout % 128 == 0) ? 128 : 64;
   if (env_bn != 128 && Cout % 256 == 0) c.bn = 256;
   c.nst = env_st == 4 ? 4 : 3;
   c.kernel = env_k == 1 ? 1 : 2;
+  c.npw = env_npw; c.cg = env_cg;
   return c;
 }
 static size_t conv_smem(int bn, int nst) { return (size_t)nst * (BM * BK * 2) + (size_t)nst * ((size_t)bn * BK * 2) + 8 * (2 * nst + 1) + 16; }
@@ -639,8 +653,13 @@ static int launch_conv(const ConvCfg& c, dim3 grid, cudaStream_t st, const bf16*
   const size_t smem = conv_smem(c.bn, c.nst);
 #define LAUNCH_CONV(BN_, ST_)                                                                                                        \
   do {                                                                                                                               \
-    QCK(cudaFuncSetAttribute(k_conv_tc<BN_, ST_, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
-    k_conv_tc<BN_, ST_, EPI><<<grid, 160, smem, st>>>(x, w, bias, y, partials, resid, ss, out, H, W, Cin, Cout, ks);                   \
+    if (c.npw == 8) {                                                                                                                \
+      QCK(cudaFuncSetAttribute(k_conv_tc<BN_, ST_, EPI, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+      k_conv_tc<BN_, ST_, EPI, 8><<<grid, 288, smem, st>>>(x, w, bias, y, partials, resid, ss, out, H, W, Cin, Cout, ks, c.cg);       \
+    } else {                                                                                                                         \
+      QCK(cudaFuncSetAttribute(k_conv_tc<BN_, ST_, EPI, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+      k_conv_tc<BN_, ST_, EPI, 4><<<grid, 160, smem, st>>>(x, w, bias, y, partials, resid, ss, out, H, W, Cin, Cout, ks, c.cg);       \
+    }                                                                                                                                \
   } while (0)
   if (c.bn == 256) { if (c.nst == 3) LAUNCH_CONV(256, 3); else LAUNCH_CONV(256, 4); }
   else if (c.bn == 128) { if (c.nst == 3) LAUNCH_CONV(128, 3); else LAUNCH_CONV(128, 4); }

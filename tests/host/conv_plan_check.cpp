@@ -10,15 +10,16 @@
 
 struct Shape { int H, W, Cin, Cout, ks; };
 
+template <int RS>
 static long check(const Shape& s, int BLOCK_N, int STAGES) {
   const int HW = s.H * s.W, pad = s.ks / 2, taps = s.ks * s.ks, kchunks = s.Cin / QP_BK, nk = taps * kchunks;
   const int A_STAGE = QP_BM * QP_BK * 2, B_STAGE = BLOCK_N * QP_BK * 2;
   long n = 0;
   for (int m0 = 0; m0 < HW; m0 += QP_BM)
     for (int n0 = 0; n0 < s.Cout; n0 += BLOCK_N)
-      for (int tid = 0; tid < 128; tid++) {
+      for (int tid = 0; tid < 8 * RS; tid++) {
         ConvPlan p;
-        conv_plan_init(p, tid, m0, n0, s.H, s.W, s.Cin, s.ks);
+        conv_plan_init<RS>(p, tid, m0, n0, s.H, s.W, s.Cin, s.ks);
         const int chunk = tid & 7, rbase = tid >> 3;
         for (int kn = 0; kn < nk; kn++) {
           // ---- definition (first kernel version)
@@ -30,14 +31,14 @@ static long check(const Shape& s, int BLOCK_N, int STAGES) {
             return -1;
           }
           const ptrdiff_t a0 = conv_plan_a(p, s.W, s.Cin);
-          for (int i = 0; i < 8; i++) {
-            const int row = rbase + 16 * i, mm = m0 + row;
+          for (int i = 0; i < QP_BM / RS; i++) {
+            const int row = rbase + RS * i, mm = m0 + row;
             const int oh = mm / s.W, ow = mm % s.W, ih = oh + dh, iw = ow + dw;
             const bool ok = mm < HW && ih >= 0 && ih < s.H && iw >= 0 && iw < s.W;
             const ptrdiff_t src = (((ptrdiff_t)ih * s.W + iw) * s.Cin + c0 + chunk * 8) * 2;
             const unsigned dst = (unsigned)(sn * A_STAGE + row * 128 + ((chunk ^ (row & 7)) << 4));
             const bool pok = (p.vmask[i] >> p.tap) & 1u;
-            const unsigned pdst = (unsigned)(p.sn * A_STAGE) + p.dstoff + (unsigned)i * 2048u;
+            const unsigned pdst = (unsigned)(p.sn * A_STAGE) + p.dstoff + (unsigned)i * (RS * 128u);
             if (pok != ok || pdst != dst || (ok && a0 + i * p.a_stride != src)) {
               printf("A mismatch: shape %dx%d cin %d ks %d m0 %d tid %d kn %d i %d ok %d/%d dst %u/%u src %td/%td\n", s.H, s.W, s.Cin, s.ks, m0, tid, kn, i,
                      (int)pok, (int)ok, pdst, dst, a0 + i * p.a_stride, src);
@@ -47,11 +48,11 @@ static long check(const Shape& s, int BLOCK_N, int STAGES) {
             n++;
           }
           const ptrdiff_t b0 = conv_plan_b(p, kn);
-          for (int i = 0; i < BLOCK_N / 16; i++) {
-            const int row = rbase + 16 * i;
+          for (int i = 0; i < BLOCK_N / RS; i++) {
+            const int row = rbase + RS * i;
             const ptrdiff_t src = ((((ptrdiff_t)(n0 + row)) * taps + tap) * s.Cin + c0 + chunk * 8) * 2;
             const unsigned dst = (unsigned)(sn * B_STAGE + row * 128 + ((chunk ^ (row & 7)) << 4));
-            const unsigned pdst = (unsigned)(p.sn * B_STAGE) + p.dstoff + (unsigned)i * 2048u;
+            const unsigned pdst = (unsigned)(p.sn * B_STAGE) + p.dstoff + (unsigned)i * (RS * 128u);
             if (pdst != dst || b0 + i * p.b_stride != src || src + 16 > (ptrdiff_t)s.Cout * taps * s.Cin * 2) {
               printf("B mismatch: cin %d cout %d ks %d n0 %d tid %d kn %d i %d dst %u/%u src %td/%td\n", s.Cin, s.Cout, s.ks, n0, tid, kn, i, pdst, dst,
                      b0 + i * p.b_stride, src);
@@ -78,9 +79,9 @@ int main() {
     for (int bn : {64, 128, 256}) {
       if (s.Cout % bn) continue;
       for (int st : {3, 4}) {
-        long n = check(s, bn, st);
-        if (n < 0) return 1;
-        total += n;
+        long n = check<16>(s, bn, st), n2 = check<32>(s, bn, st);  // 4 and 8 producer warps
+        if (n < 0 || n2 < 0) return 1;
+        total += n + n2;
       }
     }
   printf("conv plan: %ld copies identical to the definition\n", total);
