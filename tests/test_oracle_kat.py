@@ -119,6 +119,26 @@ def test_objects_rest_on_table(orc, scene_a):
     assert np.abs(orc.qpos[:7] - HOME).max() < 0.02  # PD control holds the arm against gravity within the sag
 
 
+def test_contact_forces_carry_the_weight_at_rest(orc, scene_a):
+    """Newton's third law at rest: the generalised constraint force on every resting object is exactly its weight (vertical), with no
+    horizontal component and no torque (friction rows inactive), and the solved acceleration is zero - an analytic fixed point of
+    the soft-contact model that holds whatever the impedance parameters are"""
+    blob, A, _ = scene_a
+    orc.reset(reset_qpos_scene_a(A, 0))
+    orc.stay(1000)
+    orc.forward()
+    qfc, qacc = orc.field("qfrc_constraint"), orc.field("qacc")
+    g = abs(float(np.asarray(A["opt_gravity"]).ravel()[2]))
+    first = int(np.asarray(A["nbody"]).ravel()[0]) - 6
+    for b in range(first, first + 6):
+        d, m = int(A["body_dofadr"][b]), float(A["body_mass"][b])
+        assert abs(qfc[d + 2] - m * g) < 1e-8 * m * g + 1e-10, (b, qfc[d + 2], m * g)
+        assert np.abs(qfc[d:d + 2]).max() < 1e-8 and np.abs(qfc[d + 3:d + 6]).max() < 1e-8
+        assert np.abs(qacc[d:d + 6]).max() < 1e-8
+    con = orc.contacts()
+    assert len(con) >= 6 and (con[:, 0] < 1e-3 + 1e-9).all()  # every reported contact is inside the 1 mm margin
+
+
 def test_newton_satisfies_kkt_where_pgs_does_not(orc, scene_a):
     """The MJCF sets no solver -> MuJoCo's Newton (UR5gripper_2_finger.xml:19-22).  On this model PGS with the MJCF budget of
     100 iterations is far from converged at first finger contact, Newton reaches the optimum (solver decision)."""
