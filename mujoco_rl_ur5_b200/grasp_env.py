@@ -120,8 +120,51 @@ class GraspEnv(utils.EzPickle):
     def transform_height(self, height_action, depth_height):
         return np.round(self.TABLE_HEIGHT + height_action * (0.1) / self.action_space.nvec[1], decimals=3)
 
+    def move_and_grasp_recorded(self, coordinates, rotation, directory="."):
+        """`record_grasps=True` (GraspingEnv.py:329-335): the reference photographs a successful grasp with the `side` camera at
+        1000 x 1000 while the object still hangs in the closed gripper, i.e. between the final finger check and the re-opening, and
+        writes `Grasp_{n}.png`.  The one-kernel grasp program cannot stop there, so this variant issues the same movements one by one
+        through the controller (each still a device loop) and takes the picture at that point.  Returns (grasped, png path or None)."""
+        c = self.controller
+        xyz = np.asarray(coordinates, dtype=np.float64)
+        above, centre, drop = [xyz[0], xyz[1], 1.1], [0.0, -0.6, 1.1], [0.6, 0.0, 1.15]
+        kw = dict(quiet=True, render=False)
+        res = c.move_ee(above, max_steps=1000, tolerance=0.05, **kw)
+        if res.startswith("No"):
+            res = c.move_ee(centre, max_steps=1000, tolerance=0.05, **kw)
+        holding = False
+        if not res.startswith("max"):  # stuck on the way: no attempt (GraspingEnv.py:240-246)
+            self.rotate_wrist_3_joint_to_value(self.rotations[rotation])
+            c.open_gripper(half=True, **kw)
+            low = [xyz[0], xyz[1], max(self.TABLE_HEIGHT, xyz[2] - 0.01)]
+            if not c.move_ee(low, max_steps=300, tolerance=0.01, **kw).startswith("max"):
+                c.stay(100)
+                holding = c.grasp(**kw)
+        c.actuators[0][4].Kp = 10.0
+        c.move_ee(centre, max_steps=1000, tolerance=0.05, **kw)
+        c.move_ee(drop, max_steps=1200, tolerance=0.01, **kw)
+        check = c.close_gripper(max_steps=1000, **kw) if holding else "Skipped"
+        grasped = bool(holding and check.startswith("max"))
+        png = None
+        if grasped:
+            rgb, _ = c.get_image_data(width=1000, height=1000, camera="side")
+            self.grasp_counter += 1
+            png = os.path.join(directory, "Grasp_{}.png".format(self.grasp_counter))
+            from PIL import Image  # (the reference: cv.imwrite of the colour-swapped array = the same RGB picture)
+
+            Image.fromarray(np.ascontiguousarray(rgb)).save(png)
+        c.open_gripper(**kw)
+        if grasped:
+            c.stay(200)
+        self.rotate_wrist_3_joint_to_value(0)
+        c.actuators[0][4].Kp = 20.0
+        self._print(colored("Successful grasp!", color="green", attrs=["bold"]) if grasped else colored("Did not grasp anything.", color="red", attrs=["bold"]))
+        return grasped, png
+
     def move_and_grasp(self, coordinates, rotation, render=False, record_grasps=False, markers=False, plot=False):
         """Whole 11-phase attempt as ONE device program (ge_grasp), then the reference's result summary."""
+        if record_grasps:
+            return self.move_and_grasp_recorded(coordinates, rotation)[0]
         eng = self.engine
         self.controller._push_targets()
         eng.grasp(np.asarray(coordinates, dtype=np.float64).reshape(1, 3), np.array([rotation], dtype=np.int32), self.TABLE_HEIGHT)
@@ -144,8 +187,6 @@ class GraspEnv(utils.EzPickle):
         self.last_grasp_info = inf
         if int(reward[0]):
             self._print(colored("Successful grasp!", color="green", attrs=["bold"]))
-            if record_grasps:
-                self.grasp_counter += 1
             return True
         self._print(colored("Did not grasp anything.", color="red", attrs=["bold"]))
         return False

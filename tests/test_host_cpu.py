@@ -147,3 +147,88 @@ def test_two_rank_gloo_gather(tmp_path):
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_recorded_grasp_issues_the_reference_movement_sequence(tmp_path):
+    """record_grasps=True path of the façade (GraspingEnv.py:205-386 issued phase by phase so the side-camera picture can be taken
+    between the final finger check and the re-opening, :329-335): call order, targets, step budgets and tolerances against the
+    reference function, with a scripted controller (no GPU)."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "mujoco_rl_ur5_b200", "compat"))
+    from mujoco_rl_ur5_b200.grasp_env import GraspEnv
+
+    class Gain:
+        Kp = 20.0
+
+    class Fake:
+        def __init__(self, script):
+            self.calls, self.script = [], script
+            self.actuators = [[None, None, None, None, Gain()]]
+            self.current_target_joint_values = np.zeros(7)
+
+        def _r(self, name, default="success"):
+            return self.script.get(name, default)
+
+        def move_ee(self, xyz, max_steps=None, tolerance=None, **kw):
+            self.calls.append(("move_ee", [round(float(v), 4) for v in xyz], max_steps, tolerance))
+            return self._r("move_ee%d" % sum(c[0] == "move_ee" for c in self.calls))
+
+        def move_group_to_joint_target(self, tolerance=None, max_steps=None, **kw):
+            self.calls.append(("wrist", round(float(self.current_target_joint_values[5]), 4), max_steps, tolerance))
+            return "success"
+
+        def open_gripper(self, half=False, **kw):
+            self.calls.append(("open", half, self.actuators[0][4].Kp))
+            return "success"
+
+        def grasp(self, **kw):
+            self.calls.append(("grasp",))
+            return self._r("grasp", True)
+
+        def close_gripper(self, max_steps=None, **kw):
+            self.calls.append(("close", max_steps))
+            return self._r("close", "max. steps reached: 1000")
+
+        def stay(self, ms, **kw):
+            self.calls.append(("stay", ms))
+
+        def get_image_data(self, width=200, height=200, camera="top_down", **kw):
+            self.calls.append(("image", camera, width, height))
+            img = np.zeros((height, width, 3), np.uint8)
+            img[..., 0] = 200
+            return img, np.zeros((height, width), np.float32)
+
+    def make(script):
+        e = GraspEnv.__new__(GraspEnv)
+        e.controller, e.rotations, e.TABLE_HEIGHT, e.grasp_counter, e.quiet, e.render = Fake(script), {0: 0, 3: 90}, 0.91, 0, True, False
+        return e
+
+    # a successful grasp: picture taken after the 1000-step finger check and before the gripper opens
+    e = make({})
+    ok, png = e.move_and_grasp_recorded(np.array([0.1, -0.55, 0.95]), 3, directory=str(tmp_path))
+    names = [c[0] for c in e.controller.calls]
+    assert ok and names == ["move_ee", "wrist", "open", "move_ee", "stay", "grasp", "move_ee", "move_ee", "close", "image", "open", "stay", "wrist"]
+    c = e.controller.calls
+    assert c[0] == ("move_ee", [0.1, -0.55, 1.1], 1000, 0.05) and c[1] == ("wrist", round(np.pi / 2, 4), 500, 0.05) and c[2][:2] == ("open", True)
+    assert c[3] == ("move_ee", [0.1, -0.55, 0.94], 300, 0.01) and c[4] == ("stay", 100)
+    assert c[6] == ("move_ee", [0.0, -0.6, 1.1], 1000, 0.05) and c[7] == ("move_ee", [0.6, 0.0, 1.15], 1200, 0.01)
+    assert c[8] == ("close", 1000) and c[9] == ("image", "side", 1000, 1000) and c[10] == ("open", False, 10.0) and c[11] == ("stay", 200)
+    assert c[12][1] == 0.0 and e.controller.actuators[0][4].Kp == 20.0
+    from PIL import Image
+
+    im = Image.open(png)
+    assert os.path.basename(png) == "Grasp_1.png" and im.size == (1000, 1000) and im.getpixel((5, 5)) == (200, 0, 0)
+    # grasp height clamps at the table; unreachable target falls back to the centre; a stuck approach skips the attempt
+    e = make({"move_ee1": "No valid joint angles received, could not move EE to position.", "grasp": False})
+    ok, png = e.move_and_grasp_recorded(np.array([0.3, -0.9, 0.90]), 0, directory=str(tmp_path))
+    c = e.controller.calls
+    assert not ok and png is None and c[1] == ("move_ee", [0.0, -0.6, 1.1], 1000, 0.05) and c[4] == ("move_ee", [0.3, -0.9, 0.91], 300, 0.01)
+    assert "close" not in [x[0] for x in c] and "image" not in [x[0] for x in c]
+    e = make({"move_ee1": "max. steps reached: 1000"})
+    ok, _ = e.move_and_grasp_recorded(np.array([0.0, -0.6, 0.95]), 0, directory=str(tmp_path))
+    assert not ok and [x[0] for x in e.controller.calls] == ["move_ee", "move_ee", "move_ee", "open", "wrist"]
+    # object lost on the way to the drop position: the finger check closes completely ("success") -> no reward, no picture
+    e = make({"close": "success"})
+    ok, png = e.move_and_grasp_recorded(np.array([0.0, -0.6, 0.95]), 0, directory=str(tmp_path))
+    assert not ok and png is None and ("stay", 200) not in e.controller.calls
