@@ -625,15 +625,15 @@ extern "C" const char* gq_version(void) { return "grasp_qnet 0.3 sm_100a bf16 tc
 
 // tile shape: 128 output pixels x 64 / 128 / 256 output channels (the widest that divides Cout), 3 shared-memory stages so that two
 // CTAs share an SM at BLOCK_N <= 128 (r01 sweep with the v1 kernel, whole forward: BN<=128/ST4 179, BN<=128/ST3 214, BN<=256/ST4 206,
-// BN<=256/ST3 217 TFLOP/s).  Tuning overrides: GQ_BN=128, GQ_ST=4, GQ_NPW=8 (producer warps), GQ_CGB=1 (weights bypass L1), GQ_KERNEL=1 (first kernel version).
+// BN<=256/ST3 217 TFLOP/s).  Tuning overrides: GQ_BN=128, GQ_ST=4, GQ_NPW=4 (producer warps, default 8), GQ_CGB=1 (weights bypass L1), GQ_KERNEL=1 (first kernel version).
 struct ConvCfg { int bn, nst, kernel, npw, cg; };
 static ConvCfg conv_cfg(int Cout) {
-  static int env_bn = -1, env_st = -1, env_k = -1, env_npw = 4, env_cg = 0;
+  static int env_bn = -1, env_st = -1, env_k = -1, env_npw = 8, env_cg = 0;
   if (env_bn < 0) {
     const char* e = getenv("GQ_BN"); env_bn = e ? atoi(e) : 0;
     e = getenv("GQ_ST"); env_st = e ? atoi(e) : 0;
     e = getenv("GQ_KERNEL"); env_k = e ? atoi(e) : 2;
-    e = getenv("GQ_NPW"); env_npw = (e && atoi(e) == 8) ? 8 : 4;
+    e = getenv("GQ_NPW"); env_npw = (e && atoi(e) == 4) ? 4 : 8;  // r01i sweep, whole forward: 4 warps 366, 8 warps 381 TFLOP/s
     e = getenv("GQ_CGB"); env_cg = (e && atoi(e) != 0) ? 1 : 0;
   }
   ConvCfg c;
