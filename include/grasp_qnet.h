@@ -41,6 +41,10 @@ int gq_upsample2x(const void* x, void* y, int B, int H, int W, int C, void* stre
 /* Grasping_Module_multidiscrete.C1 = nn.Conv2d(64, A, 1) + squeeze + Sigmoid (Modules.py:251,281-283): x [B,HW,64] bf16, w [A][64] f32,
  * bias [A] f32 -> q [B,A,HW] f32 (the reference's NCHW output layout) */
 int gq_head(const void* x, const float* w, const float* bias, float* q, int B, int HW, int A, void* stream);
+/* The same tail computed at the lower resolution: Grasping_Module_multidiscrete ends with UP2 -> C1 -> sigmoid (Modules.py:250-251,281-283) and
+ * C1 (1x1 conv + bias) commutes with bilinear up-sampling, so q = sigmoid(UP2(C1(x))): x [B,H,W,64] bf16 (the input of UP2),
+ * scratch_z [B,A,H,W] f32, q [B,A,2H,2W] f32 */
+int gq_head_up2(const void* x, const float* w, const float* bias, float* scratch_z, float* q, int B, int H, int W, int A, void* stream);
 /* Grasp_Agent.transform_observation(normalize=True, jitter_and_noise=False) batched (Grasping_Agent_multidiscrete.py:301-368):
  * rgb [B,HW,3] u8, depth [B,HW] f32 metres -> state [B,4,HW] f32 (rgb/255, depth clipped at depth_threshold, negated, min-max per image);
  * scratch_minmax [B,2] f32 */

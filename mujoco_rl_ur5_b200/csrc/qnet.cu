@@ -414,10 +414,16 @@ __global__ void k_bn_reduce(const float* __restrict__ part, float* __restrict__ 
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   int b = i / C, c = i % C;
-  double s1 = 0, s2 = 0;
-  const float* p = part + ((size_t)b * nparts * C + c) * 2;
-  for (int k = 0; k < nparts; k++) { s1 += p[(size_t)k * C * 2]; s2 += p[(size_t)k * C * 2 + 1]; }
-  stats[(size_t)i * 2] = (float)s1; stats[(size_t)i * 2 + 1] = (float)s2;
+  // four interleaved double accumulators (parts k % 4), combined as (a0 + a1) + (a2 + a3): a fixed order, four times shorter dependency chain
+  double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  const float2* p = (const float2*)part + (size_t)b * nparts * C + c;
+  int k = 0;
+  for (; k + 4 <= nparts; k += 4) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) { const float2 v = __ldg(p + (size_t)(k + j) * C); s1[j] += v.x; s2[j] += v.y; }
+  }
+  for (int j = 0; k < nparts; k++, j++) { const float2 v = __ldg(p + (size_t)k * C); s1[j] += v.x; s2[j] += v.y; }
+  stats[(size_t)i * 2] = (float)((s1[0] + s1[1]) + (s1[2] + s1[3])); stats[(size_t)i * 2 + 1] = (float)((s2[0] + s2[1]) + (s2[2] + s2[3]));
 }
 
 // ------------------------------------------------------------------------------------------------ small layers
@@ -453,6 +459,49 @@ __global__ void k_conv_first(const float* __restrict__ x, const float* __restric
       o[h] = __floats2bfloat162_rn(a0, a1);
     }
     *(uint4*)(out + co) = *(uint4*)o;
+  }
+}
+// same layer, two horizontally consecutive pixels per thread: every weight vector read from shared memory feeds both (half the LDS
+// traffic per FMA, the limiter of the one-pixel version); pixel pairs are taken along the flattened index, B*H*W must be even
+__global__ void __launch_bounds__(128) k_conv_first2(const float* __restrict__ x, const float* __restrict__ w, bf16* __restrict__ y, int B, int H, int W) {
+  __shared__ __align__(16) float sw[64 * 36];
+  for (int i = threadIdx.x; i < 64 * 36; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int HW = H * W;
+  const int p0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (p0 >= B * HW) return;
+  float in[2][36];
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    const int p = p0 + q, b = p / HW, oh = (p % HW) / W, ow = p % W;
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+      const int ih = oh + t / 3 - 1, iw = ow + t % 3 - 1;
+      const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+#pragma unroll
+      for (int c = 0; c < 4; c++) in[q][t * 4 + c] = ok ? __ldg(x + ((size_t)(b * 4 + c) * H + ih) * W + iw) : 0.f;
+    }
+  }
+  bf16* out = y + (size_t)p0 * 64;
+  const float4* sw4 = (const float4*)sw;
+  for (int co = 0; co < 64; co += 8) {
+    __nv_bfloat162 o[2][4];
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+      float a[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        const float4 w0 = sw4[(co + 2 * h) * 9 + k], w1 = sw4[(co + 2 * h + 1) * 9 + k];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {  // same accumulation order per output as k_conv_first
+          a[q][0] += in[q][4 * k] * w0.x; a[q][0] += in[q][4 * k + 1] * w0.y; a[q][0] += in[q][4 * k + 2] * w0.z; a[q][0] += in[q][4 * k + 3] * w0.w;
+          a[q][1] += in[q][4 * k] * w1.x; a[q][1] += in[q][4 * k + 1] * w1.y; a[q][1] += in[q][4 * k + 2] * w1.z; a[q][1] += in[q][4 * k + 3] * w1.w;
+        }
+      }
+      o[0][h] = __floats2bfloat162_rn(a[0][0], a[0][1]); o[1][h] = __floats2bfloat162_rn(a[1][0], a[1][1]);
+    }
+    *(uint4*)(out + co) = *(uint4*)o[0];
+    *(uint4*)(out + 64 + co) = *(uint4*)o[1];
   }
 }
 // MaxPool2d(kernel 3, stride 2, padding 1) on NHWC bf16
@@ -540,6 +589,8 @@ __global__ void k_upsample2x(const bf16* __restrict__ x, bf16* __restrict__ y, i
   *(uint4*)(y + p * C + cv) = *(uint4*)o;
 }
 // last layer: conv1x1 64 -> A (+bias) and sigmoid; x [B,HW,64] bf16, w [A][64] f32 -> q [B,A,HW] f32 (NCHW like the reference output)
+// SIGMOID = false writes the pre-activation (used at low resolution by gq_head_up2)
+template <bool SIGMOID>
 __global__ void k_head(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ q, int B, int HW, int A) {
   __shared__ __align__(16) float sw[8 * 64 + 8];
   for (int i = threadIdx.x; i < A * 64; i += blockDim.x) sw[i] = w[i];
@@ -549,9 +600,14 @@ __global__ void k_head(const bf16* __restrict__ x, const float* __restrict__ w, 
   if (p >= (size_t)B * HW) return;
   int b = p / HW, pix = p % HW;
   float in[64];
-  const __nv_bfloat162* src = (const __nv_bfloat162*)(x + p * 64);
+  const uint4* src = (const uint4*)(x + p * 64);  // the pixel's 64 channels = 8 x 16 bytes
 #pragma unroll
-  for (int c = 0; c < 32; c++) { float2 v = __bfloat1622float2(src[c]); in[2 * c] = v.x; in[2 * c + 1] = v.y; }
+  for (int c = 0; c < 8; c++) {
+    const uint4 qv = __ldg(src + c);
+    const __nv_bfloat162* pv = (const __nv_bfloat162*)&qv;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { float2 v = __bfloat1622float2(pv[k]); in[8 * c + 2 * k] = v.x; in[8 * c + 2 * k + 1] = v.y; }
+  }
   for (int a = 0; a < A; a++) {
     float acc = sw[8 * 64 + a];
 #pragma unroll
@@ -559,8 +615,25 @@ __global__ void k_head(const bf16* __restrict__ x, const float* __restrict__ w, 
       float4 wv = ((const float4*)sw)[a * 16 + c];
       acc += in[4 * c] * wv.x; acc += in[4 * c + 1] * wv.y; acc += in[4 * c + 2] * wv.z; acc += in[4 * c + 3] * wv.w;
     }
-    q[((size_t)b * A + a) * HW + pix] = 1.f / (1.f + __expf(-acc));
+    q[((size_t)b * A + a) * HW + pix] = SIGMOID ? 1.f / (1.f + __expf(-acc)) : acc;
   }
+}
+// q = sigmoid(UpsamplingBilinear2d(2)(z)) on A planes: z [B*A, H, W] f32 -> q [B*A, 2H, 2W] f32 (align_corners=True).
+// The network ends with UP2 -> C1 (1x1 conv + bias) -> sigmoid (Modules.py:250-251,281-283); a 1x1 convolution is linear per pixel and the
+// bilinear weights sum to one, so C1(UP2(x)) == UP2(C1(x)): the head runs on the 4x smaller map and only its A planes are up-sampled
+__global__ void k_up2_sigmoid(const float* __restrict__ z, float* __restrict__ q, int planes, int H, int W) {
+  const int OH = 2 * H, OW = 2 * W;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)planes * OH * OW;
+  if (i >= n) return;
+  const int ow = i % OW, oh = (i / OW) % OH;
+  const size_t pl = i / ((size_t)OW * OH);
+  const float fy = oh * (float)(H - 1) / (float)(OH - 1), fx = ow * (float)(W - 1) / (float)(OW - 1);
+  const int y0 = (int)fy, x0 = (int)fx, y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float wy = fy - y0, wx = fx - x0;
+  const float* zp = z + pl * H * W;
+  const float a = __ldg(zp + y0 * W + x0), b = __ldg(zp + y0 * W + x1), c = __ldg(zp + y1 * W + x0), d = __ldg(zp + y1 * W + x1);
+  const float v = (a * (1 - wx) + b * wx) * (1 - wy) + (c * (1 - wx) + d * wx) * wy;
+  q[i] = 1.f / (1.f + __expf(-v));
 }
 // flat arg-max over the A*HW Q-values of every image (Grasping_Agent_multidiscrete.py:295-299): idx = rot*HW + y*W + x
 __global__ void __launch_bounds__(1024) k_argmax(const float* __restrict__ q, int n, int* __restrict__ idx, float* __restrict__ val) {
@@ -711,7 +784,10 @@ extern "C" int gq_conv_tc_block_out(const void* x, const void* w, const float* b
   return 0;
 }
 extern "C" int gq_conv_first(const float* x, const float* w, void* y, int B, int H, int W, void* stream) {
-  k_conv_first<<<(B * H * W + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, w, (bf16*)y, B, H, W);
+  static int one_pixel = -1;
+  if (one_pixel < 0) { const char* e = getenv("GQ_FIRST1"); one_pixel = (e && atoi(e) != 0) ? 1 : 0; }  // GQ_FIRST1=1: one pixel per thread
+  if (one_pixel || ((size_t)B * H * W) % 2) k_conv_first<<<(B * H * W + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, w, (bf16*)y, B, H, W);
+  else k_conv_first2<<<(B * H * W / 2 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, w, (bf16*)y, B, H, W);
   QCK(cudaGetLastError());
   return 0;
 }
@@ -742,7 +818,16 @@ extern "C" int gq_upsample2x(const void* x, void* y, int B, int H, int W, int C,
 }
 extern "C" int gq_head(const void* x, const float* w, const float* bias, float* q, int B, int HW, int A, void* stream) {
   if (A > 8) { snprintf(q_err, sizeof q_err, "gq_head: at most 8 action channels"); return -1; }
-  k_head<<<(unsigned)(((size_t)B * HW + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const bf16*)x, w, bias, q, B, HW, A);
+  k_head<true><<<(unsigned)(((size_t)B * HW + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const bf16*)x, w, bias, q, B, HW, A);
+  QCK(cudaGetLastError());
+  return 0;
+}
+extern "C" int gq_head_up2(const void* x, const float* w, const float* bias, float* scratch_z, float* q, int B, int H, int W, int A, void* stream) {
+  if (A > 8 || !scratch_z) { snprintf(q_err, sizeof q_err, "gq_head_up2: bad argument"); return -1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  k_head<false><<<(unsigned)(((size_t)B * H * W + 127) / 128), 128, 0, st>>>((const bf16*)x, w, bias, scratch_z, B, H * W, A);
+  size_t n = (size_t)B * A * 4 * H * W;
+  k_up2_sigmoid<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scratch_z, q, B * A, H, W);
   QCK(cudaGetLastError());
   return 0;
 }

@@ -20,7 +20,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 QLIB_PATH = os.path.join(_HERE, "csrc", "libgrasp_qnet.so")
 _QLIB = None
-QSYMBOLS = ["gq_last_error", "gq_version", "gq_conv_tc", "gq_conv_tc_block_out", "gq_conv_first", "gq_maxpool", "gq_bn_act", "gq_upsample2x", "gq_head", "gq_argmax", "gq_obs_to_state"]
+QSYMBOLS = ["gq_last_error", "gq_version", "gq_conv_tc", "gq_conv_tc_block_out", "gq_conv_first", "gq_maxpool", "gq_bn_act", "gq_upsample2x", "gq_head", "gq_head_up2", "gq_argmax", "gq_obs_to_state"]
 
 
 def load_qnet_library():
@@ -39,6 +39,7 @@ def load_qnet_library():
         L.gq_bn_act.argtypes = [P, P, P, P, P, P, I, I, I, F, P]
         L.gq_upsample2x.argtypes = [P, P, I, I, I, I, P]
         L.gq_head.argtypes = [P, P, P, P, I, I, I, P]
+        L.gq_head_up2.argtypes = [P, P, P, P, P, I, I, I, I, P]
         L.gq_argmax.argtypes = [P, I, I, P, P, P]
         L.gq_obs_to_state.argtypes = [P, P, F, P, P, I, I, P]
         _QLIB = L
@@ -129,6 +130,8 @@ class QNetForward:
             self.blocks.append(b)
         # BasicBlock tail: shortcut conv + BN-apply of the main branch + add + ReLU in one kernel (GQ_FUSE_TAIL=0: separate kernels)
         self.fuse_tail = os.environ.get("GQ_FUSE_TAIL", "1") != "0"
+        # network tail: head on the 100x100 map, then up-sample its 6 planes (GQ_FUSE_HEAD=0: up-sample 64 channels, then the head)
+        self.fuse_head = os.environ.get("GQ_FUSE_HEAD", "1") != "0"
         self.w_head = sd["1.C1.weight"].reshape(self.A, 64).contiguous()
         self.b_head = sd["1.C1.bias"].contiguous()
         self.launches = 0
@@ -208,9 +211,14 @@ class QNetForward:
         x = self.basic_block(x, self.blocks[4], B, h2, w2)          # 1.RB2 256->128
         x = self.upsample(x.view(B, h2, w2, 128), B, h2, w2, 128)   # -> 100
         x = self.basic_block(x, self.blocks[5], B, 2 * h2, 2 * w2)  # 1.RB3 128->64
+        q = t.empty((B, self.A, 4 * h2, 4 * w2), dtype=t.float32, device=self.dev)
+        if self.fuse_head:
+            z = t.empty((B, self.A, 2 * h2, 2 * w2), dtype=t.float32, device=self.dev)
+            self._ck(self.L.gq_head_up2(self._p(x), self._p(self.w_head), self._p(self.b_head), self._p(z), self._p(q), B, 2 * h2, 2 * w2, self.A, self._stream()),
+                     "gq_head_up2")
+            return q
         x = self.upsample(x.view(B, 2 * h2, 2 * w2, 64), B, 2 * h2, 2 * w2, 64)  # -> 200
         HW = 16 * h2 * w2
-        q = t.empty((B, self.A, 4 * h2, 4 * w2), dtype=t.float32, device=self.dev)
         self._ck(self.L.gq_head(self._p(x), self._p(self.w_head), self._p(self.b_head), self._p(q), B, HW, self.A, self._stream()), "gq_head")
         return q
 
