@@ -8,11 +8,13 @@
 // never puts the policy net in eval() and forwards one image at a time.
 //
 // C-ABI: see include/grasp_qnet.h.  No CPU fallback.
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked)
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "../../include/grasp_qnet.h"
 #include "qnet_plan.h"
@@ -106,6 +108,15 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, uint
 }
 __device__ __forceinline__ void cp_async16_s(uint32_t dst_smem_addr, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem_addr), "l"(src), "r"(src_bytes) : "memory");
+}
+// TMA: one thread copies a whole [rows x 64 bf16] box of a 2-D tensor into a 128-byte-swizzled shared-memory tile; completion is
+// reported to the mbarrier as transferred bytes (complete_tx), so the same "full" barrier collects the cp.async arrivals and the TMA
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem_addr, const CUtensorMap* tmap, int x, int y, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst_smem_addr), "l"((uint64_t)tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 // .cg: cache in L2 only (weight tiles are read once per CTA; keeping them out of L1 leaves it to the activation rows the 9 taps re-read)
 __device__ __forceinline__ void cp_async16_cg(uint32_t dst_smem_addr, const void* src) {
@@ -263,8 +274,11 @@ __global__ void __launch_bounds__(160) k_conv_tc_v1(const bf16* __restrict__ x, 
 //    BN-apply kernel per block (BasicBlock.forward, Modules.py:128-142)
 //  * NPW = 4 or 8 producer warps (GQ_NPW): 8 halves the copies per thread and lets warps 4-7 take half of the epilogue columns (a warp
 //    may read the TMEM lane quarter warp % 4, so warps w and w + 4 share rows and split columns)
-template <int BLOCK_N, int STAGES, int EPI, int NPW>
-__global__ void __launch_bounds__(32 * (NPW + 1)) k_conv_tc(const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ bias,
+//  * TMAB = 1 (GQ_TMA=1): the weight tile of a k-step (two thirds of the bytes at BLOCK_N = 256) is one TMA box issued by one thread
+//    instead of BLOCK_N / RS cp.async per producer thread; the activation gather stays on cp.async (its rows are not a box)
+template <int BLOCK_N, int STAGES, int EPI, int NPW, int TMAB>
+__global__ void __launch_bounds__(32 * (NPW + 1)) k_conv_tc(const __grid_constant__ CUtensorMap tmap_w, const bf16* __restrict__ x,
+                                                            const bf16* __restrict__ w, const float* __restrict__ bias,
                                                  float* __restrict__ y, float* __restrict__ stats, const float* __restrict__ resid,
                                                  const float2* __restrict__ scale_shift, bf16* __restrict__ out, int H, int W, int Cin, int Cout,
                                                  int ks, int cg_weights) {
@@ -281,7 +295,7 @@ __global__ void __launch_bounds__(32 * (NPW + 1)) k_conv_tc(const bf16* __restri
   const int HW = H * W, m0 = blockIdx.x * BM, n0 = blockIdx.y * BLOCK_N, b = blockIdx.z;
   const int pad = ks / 2, taps = ks * ks, kchunks = Cin / BK, nk = taps * kchunks;
   if (tid == 0) {
-    for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 32 * NPW); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 32 * NPW + TMAB); mbar_init(&empty[i], 1); }
     mbar_init(accbar, 1);
     fence_barrier_init();
   }
@@ -311,12 +325,19 @@ __global__ void __launch_bounds__(32 * (NPW + 1)) k_conv_tc(const bf16* __restri
         cp_async16_s(da + i * (RS * 128), ok ? (const void*)ap : (const void*)xb, ok ? 16u : 0u);
         ap += p.a_stride;
       }
-      const char* bp = wb + conv_plan_b(p, kn);
-      const uint32_t db = sB_u + (uint32_t)(p.sn * B_STAGE);
+      if constexpr (TMAB) {
+        if (tid == 0) {  // box = rows n0 .. n0 + BLOCK_N - 1, columns 64 kn .. 64 kn + 63 of w viewed as [Cout][taps * Cin]
+          mbar_arrive_expect_tx(&full[p.sn], (uint32_t)B_STAGE);
+          tma_load_2d(smem_u32(sB) + (uint32_t)(p.sn * B_STAGE), &tmap_w, kn * BK, n0, &full[p.sn]);
+        }
+      } else {
+        const char* bp = wb + conv_plan_b(p, kn);
+        const uint32_t db = sB_u + (uint32_t)(p.sn * B_STAGE);
 #pragma unroll
-      for (int i = 0; i < BLOCK_N / RS; i++) {
-        if (cg_weights) cp_async16_cg(db + i * (RS * 128), bp); else cp_async16_s(db + i * (RS * 128), bp, 16u);
-        bp += p.b_stride;
+        for (int i = 0; i < BLOCK_N / RS; i++) {
+          if (cg_weights) cp_async16_cg(db + i * (RS * 128), bp); else cp_async16_s(db + i * (RS * 128), bp, 16u);
+          bp += p.b_stride;
+        }
       }
       cp_async_mbar_arrive(&full[p.sn]);
       conv_plan_next(p, STAGES, kchunks, pad);
@@ -698,46 +719,76 @@ extern "C" const char* gq_version(void) { return "grasp_qnet 0.3 sm_100a bf16 tc
 
 // tile shape: 128 output pixels x 64 / 128 / 256 output channels (the widest that divides Cout), 3 shared-memory stages so that two
 // CTAs share an SM at BLOCK_N <= 128 (r01 sweep with the v1 kernel, whole forward: BN<=128/ST4 179, BN<=128/ST3 214, BN<=256/ST4 206,
-// BN<=256/ST3 217 TFLOP/s).  Tuning overrides: GQ_BN=128, GQ_ST=4, GQ_NPW=4 (producer warps, default 8), GQ_CGB=1 (weights bypass L1), GQ_KERNEL=1 (first kernel version).
-struct ConvCfg { int bn, nst, kernel, npw, cg; };
+// BN<=256/ST3 217 TFLOP/s).  Tuning overrides: GQ_BN=128, GQ_ST=4, GQ_NPW=4 (producer warps, default 8), GQ_CGB=1 (weights bypass L1), GQ_TMA=1 (weight tiles by TMA), GQ_KERNEL=1 (first kernel version).
+struct ConvCfg { int bn, nst, kernel, npw, cg, tma; };
 static ConvCfg conv_cfg(int Cout) {
-  static int env_bn = -1, env_st = -1, env_k = -1, env_npw = 8, env_cg = 0;
+  static int env_bn = -1, env_st = -1, env_k = -1, env_npw = 8, env_cg = 0, env_tma = 0;
   if (env_bn < 0) {
     const char* e = getenv("GQ_BN"); env_bn = e ? atoi(e) : 0;
     e = getenv("GQ_ST"); env_st = e ? atoi(e) : 0;
     e = getenv("GQ_KERNEL"); env_k = e ? atoi(e) : 2;
     e = getenv("GQ_NPW"); env_npw = (e && atoi(e) == 4) ? 4 : 8;  // r01i sweep, whole forward: 4 warps 366, 8 warps 381 TFLOP/s
     e = getenv("GQ_CGB"); env_cg = (e && atoi(e) != 0) ? 1 : 0;
+    e = getenv("GQ_TMA"); env_tma = (e && atoi(e) != 0) ? 1 : 0;
   }
   ConvCfg c;
   c.bn = (Cout % 128 == 0) ? 128 : 64;
   if (env_bn != 128 && Cout % 256 == 0) c.bn = 256;
   c.nst = env_st == 4 ? 4 : 3;
   c.kernel = env_k == 1 ? 1 : 2;
-  c.npw = env_npw; c.cg = env_cg;
+  c.npw = env_npw; c.cg = env_cg; c.tma = env_tma;
+  if (c.kernel == 2) c.nst = 3;  // the second kernel is built with 3 stages only (4 measured slower, profiles/r01i_qnet_sweep.txt)
   return c;
 }
 static size_t conv_smem(int bn, int nst) { return (size_t)nst * (BM * BK * 2) + (size_t)nst * ((size_t)bn * BK * 2) + 8 * (2 * nst + 1) + 16; }
+
+// 2-D tensor map of the packed weights w [Cout][taps * Cin] bf16 with a [BLOCK_N rows x 64 columns] box, 128-byte swizzle (the layout the
+// UMMA descriptors expect); cuTensorMapEncodeTiled comes from the driver through the runtime (no libcuda link dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_weight_tmap(CUtensorMap* m, const void* w, int Cout, int K, int bn) {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+  }
+  if (!fn) { snprintf(q_err, sizeof q_err, "cuTensorMapEncodeTiled is not available"); return -3; }
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+  cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(q_err, sizeof q_err, "cuTensorMapEncodeTiled failed (%d)", (int)r); return -3; }
+  return 0;
+}
 
 // EPI 0: y (+ BN partials); EPI 1: out = relu(resid * scale + shift + conv + bias) bf16
 template <int EPI>
 static int launch_conv(const ConvCfg& c, dim3 grid, cudaStream_t st, const bf16* x, const bf16* w, const float* bias, float* y, float* partials,
                        const float* resid, const float2* ss, bf16* out, int H, int W, int Cin, int Cout, int ks) {
-  const size_t smem = conv_smem(c.bn, c.nst);
-#define LAUNCH_CONV(BN_, ST_)                                                                                                        \
+  const size_t smem = conv_smem(c.bn, 3);
+  alignas(64) CUtensorMap tm;
+  memset(&tm, 0, sizeof tm);
+  if (c.tma) { int r = make_weight_tmap(&tm, w, Cout, ks * ks * Cin, c.bn); if (r) return r; }
+#define LAUNCH_ONE(BN_, NPW_, TMA_)                                                                                                  \
   do {                                                                                                                               \
-    if (c.npw == 8) {                                                                                                                \
-      QCK(cudaFuncSetAttribute(k_conv_tc<BN_, ST_, EPI, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
-      k_conv_tc<BN_, ST_, EPI, 8><<<grid, 288, smem, st>>>(x, w, bias, y, partials, resid, ss, out, H, W, Cin, Cout, ks, c.cg);       \
-    } else {                                                                                                                         \
-      QCK(cudaFuncSetAttribute(k_conv_tc<BN_, ST_, EPI, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
-      k_conv_tc<BN_, ST_, EPI, 4><<<grid, 160, smem, st>>>(x, w, bias, y, partials, resid, ss, out, H, W, Cin, Cout, ks, c.cg);       \
-    }                                                                                                                                \
+    QCK(cudaFuncSetAttribute(k_conv_tc<BN_, 3, EPI, NPW_, TMA_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+    k_conv_tc<BN_, 3, EPI, NPW_, TMA_><<<grid, 32 * (NPW_ + 1), smem, st>>>(tm, x, w, bias, y, partials, resid, ss, out, H, W, Cin, Cout, ks, c.cg); \
   } while (0)
-  if (c.bn == 256) { if (c.nst == 3) LAUNCH_CONV(256, 3); else LAUNCH_CONV(256, 4); }
-  else if (c.bn == 128) { if (c.nst == 3) LAUNCH_CONV(128, 3); else LAUNCH_CONV(128, 4); }
-  else { if (c.nst == 3) LAUNCH_CONV(64, 3); else LAUNCH_CONV(64, 4); }
+#define LAUNCH_CONV(BN_)                                                                                                             \
+  do {                                                                                                                               \
+    if (c.npw == 8) { if (c.tma) LAUNCH_ONE(BN_, 8, 1); else LAUNCH_ONE(BN_, 8, 0); }                                                \
+    else { if (c.tma) LAUNCH_ONE(BN_, 4, 1); else LAUNCH_ONE(BN_, 4, 0); }                                                           \
+  } while (0)
+  if (c.bn == 256) LAUNCH_CONV(256);
+  else if (c.bn == 128) LAUNCH_CONV(128);
+  else LAUNCH_CONV(64);
 #undef LAUNCH_CONV
+#undef LAUNCH_ONE
   return 0;
 }
 
