@@ -418,6 +418,157 @@ __global__ void __launch_bounds__(32 * (NPW + 1)) k_conv_tc(const __grid_constan
   __syncthreads();
   if (warp == 0) tmem_dealloc(tacc, BLOCK_N);
 }
+// ---- EXPERIMENTAL (GQ_PERSIST=1, default off; written after the GPU budget of round 1 was spent: compiled, never run — the first thing
+// to test in round 2).  Persistent form of k_conv_tc: one CTA per SM walks a static round-robin list of (m tile, n tile, image) tiles,
+// the accumulator is double-buffered in TMEM (2 x BLOCK_N columns) and the epilogue has its own 4 warps, so the TMEM read-out, the stores
+// and the BatchNorm partial sums of tile i overlap the main loop of tile i + 1, and the per-tile costs of a CTA (launch, TMEM allocation,
+// barrier initialisation) are paid once.  Roles: warps 0-7 producers (cp.async activation gather, thread 0 also issues the weight TMA),
+// warp 8 lane 0 issues the MMAs, warps 9-12 are the epilogue (lane quarter = warp % 4).  The smem ring, its full / empty barriers and the
+// gather plan are those of k_conv_tc, with the stage / phase counters running across tiles; acc_full[a] (1 commit) / acc_empty[a]
+// (128 epilogue arrivals) hand the accumulator buffers back and forth.
+template <int BLOCK_N, int STAGES, int EPI>
+__global__ void __launch_bounds__(416) k_conv_tc_persist(const __grid_constant__ CUtensorMap tmap_w, const bf16* __restrict__ x, const float* __restrict__ bias,
+                                                         float* __restrict__ y, float* __restrict__ stats, const float* __restrict__ resid,
+                                                         const float2* __restrict__ scale_shift, bf16* __restrict__ out, int H, int W, int Cin, int Cout,
+                                                         int ks, int gx, int gy, int ntiles) {
+  constexpr int A_STAGE = BM * BK * 2, B_STAGE = BLOCK_N * BK * 2, NPW = 8, RS = 4 * NPW;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE;
+  uint64_t* full = (uint64_t*)(smem + STAGES * (A_STAGE + B_STAGE));
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;    // [2]
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HW = H * W, pad = ks / 2, taps = ks * ks, kchunks = Cin / BK, nk = taps * kchunks;
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 32 * NPW + 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 2 * BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tacc = *tmem_slot;
+  constexpr uint32_t idesc = make_idesc(BM, BLOCK_N);
+  if (warp < NPW) {
+    // ---- producers
+    int sn = 0, round = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int mt = t % gx, nt = (t / gx) % gy, b = t / (gx * gy);
+      const int m0 = mt * BM, n0 = nt * BLOCK_N;
+      ConvPlan p;
+      conv_plan_init<RS>(p, tid, m0, n0, H, W, Cin, ks);
+      p.sn = sn; p.round = round;  // the ring keeps turning across tiles
+      const uint32_t sA_u = smem_u32(sA) + p.dstoff;
+      const char* xb = (const char*)(x + (size_t)b * HW * Cin);
+      for (int kn = 0; kn < nk; kn++) {
+        if (p.round > 0) mbar_wait(&empty[p.sn], (uint32_t)(p.round - 1) & 1u);
+        const uint32_t tbit = 1u << p.tap;
+        const char* ap = xb + conv_plan_a(p, W, Cin);
+        const uint32_t da = sA_u + (uint32_t)(p.sn * A_STAGE);
+#pragma unroll
+        for (int i = 0; i < BM / RS; i++) {
+          const bool ok = (p.vmask[i] & tbit) != 0;
+          cp_async16_s(da + i * (RS * 128), ok ? (const void*)ap : (const void*)xb, ok ? 16u : 0u);
+          ap += p.a_stride;
+        }
+        if (tid == 0) {
+          mbar_arrive_expect_tx(&full[p.sn], (uint32_t)B_STAGE);
+          tma_load_2d(smem_u32(sB) + (uint32_t)(p.sn * B_STAGE), &tmap_w, kn * BK, n0, &full[p.sn]);
+        }
+        cp_async_mbar_arrive(&full[p.sn]);
+        conv_plan_next(p, STAGES, kchunks, pad);
+      }
+      sn = p.sn; round = p.round;
+    }
+  } else if (warp == NPW) {
+    // ---- MMA issuer
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0; int i = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
+        const int a = i & 1;
+        mbar_wait(&acc_empty[a], (uint32_t)((i >> 1) & 1) ^ 1u);  // buffer drained by the epilogue of tile i - 2 (passes at once for i < 2)
+        tc_fence_after();
+        const uint32_t dacc = tacc + (uint32_t)(a * BLOCK_N);
+        for (int kb = 0; kb < nk; kb++) {
+          mbar_wait(&full[s], ph);
+          fence_proxy_async();
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + s * A_STAGE), b_base = smem_u32(sB + s * B_STAGE);
+#pragma unroll
+          for (int k = 0; k < BK / 16; k++)
+            umma_bf16(dacc, make_smem_desc_sw128(a_base + k * 32), make_smem_desc_sw128(b_base + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty[s]);
+          if (kb == nk - 1) umma_commit(&acc_full[a]);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ---- epilogue warps 9..12: lane quarter warp % 4
+    const int quarter = warp & 3;
+    int i = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
+      const int mt = t % gx, nt = (t / gx) % gy, b = t / (gx * gy);
+      const int m0 = mt * BM, n0 = nt * BLOCK_N, a = i & 1;
+      mbar_wait(&acc_full[a], (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      const int m = m0 + quarter * 32 + lane;
+      const bool mvalid = m < HW;
+      const size_t rowoff = ((size_t)b * HW + m) * Cout + n0;
+      for (int cb = 0; cb < BLOCK_N; cb += 32) {
+        float v[32];
+        tmem_ld32(tacc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * BLOCK_N + cb), v);
+        if (bias) {
+          const float4* b4 = (const float4*)(bias + n0 + cb);
+#pragma unroll
+          for (int j = 0; j < 8; j++) { const float4 bv = __ldg(b4 + j); v[4 * j] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w; }
+        }
+        if constexpr (EPI == 0) {
+          if (mvalid) {
+            float4* dst = (float4*)(y + rowoff + cb);
+#pragma unroll
+            for (int j = 0; j < 8; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (stats) {
+            float q[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) { v[j] = mvalid ? v[j] : 0.f; q[j] = v[j] * v[j]; }
+            const float s1 = warp_colsum32(v, lane), s2 = warp_colsum32(q, lane);
+            float2* pp = (float2*)(stats + ((((size_t)b * gx + mt) * 4 + quarter) * Cout + n0 + cb) * 2);
+            pp[lane] = make_float2(s1, s2);
+          }
+        } else {
+          if (mvalid) {
+            const float4* r4 = (const float4*)(resid + rowoff + cb);
+            const float4* ss4 = (const float4*)(scale_shift + (size_t)b * Cout + n0 + cb);
+            __nv_bfloat162 o[16];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const float4 r = __ldg(r4 + j);
+              const float4 sa = __ldg(ss4 + 2 * j), sb = __ldg(ss4 + 2 * j + 1);
+              const float o0 = fmaxf(r.x * sa.x + sa.y + v[4 * j], 0.f), o1 = fmaxf(r.y * sa.z + sa.w + v[4 * j + 1], 0.f);
+              const float o2 = fmaxf(r.z * sb.x + sb.y + v[4 * j + 2], 0.f), o3 = fmaxf(r.w * sb.z + sb.w + v[4 * j + 3], 0.f);
+              o[2 * j] = __floats2bfloat162_rn(o0, o1); o[2 * j + 1] = __floats2bfloat162_rn(o2, o3);
+            }
+            uint4* dst = (uint4*)(out + rowoff + cb);
+#pragma unroll
+            for (int j = 0; j < 4; j++) dst[j] = ((const uint4*)o)[j];
+          }
+        }
+      }
+      tc_fence_before();  // the tcgen05.ld of this buffer are complete (wait::ld inside tmem_ld32): hand it back to the MMA warp
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[a])) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tacc, 2 * BLOCK_N);
+}
+
 // per-image BatchNorm (training mode, own statistics) folded into one multiply-add per channel: (scale, shift) from (sum, sum of squares)
 __global__ void k_bn_scale_shift(const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta, float2* __restrict__ ss,
                                  int B, int C, int HW, float eps) {
@@ -717,15 +868,16 @@ extern "C" const char* gq_version(void) { return "grasp_qnet 0.4 sm_100a bf16 tc
 // tile shape: 128 output pixels x 64 / 128 / 256 output channels (the widest that divides Cout), 3 shared-memory stages so that two
 // CTAs share an SM at BLOCK_N <= 128 (r01 sweep with the v1 kernel, whole forward: BN<=128/ST4 179, BN<=128/ST3 214, BN<=256/ST4 206,
 // BN<=256/ST3 217 TFLOP/s).  Tuning overrides: GQ_BN=128, GQ_ST=4, GQ_NPW=4 (producer warps, default 8), GQ_CGB=1 (weights bypass L1), GQ_TMA=0 (weight tiles by cp.async instead of TMA), GQ_KERNEL=1 (first kernel version).
-struct ConvCfg { int bn, nst, kernel, npw, cg, tma; };
+struct ConvCfg { int bn, nst, kernel, npw, cg, tma, persist; };
 static ConvCfg conv_cfg(int Cout) {
-  static int env_bn = -1, env_st = -1, env_k = -1, env_npw = 8, env_cg = 0, env_tma = 1;
+  static int env_bn = -1, env_st = -1, env_k = -1, env_npw = 8, env_cg = 0, env_tma = 1, env_persist = 0;
   if (env_bn < 0) {
     const char* e = getenv("GQ_BN"); env_bn = e ? atoi(e) : 0;
     e = getenv("GQ_ST"); env_st = e ? atoi(e) : 0;
     e = getenv("GQ_KERNEL"); env_k = e ? atoi(e) : 2;
     e = getenv("GQ_NPW"); env_npw = (e && atoi(e) == 4) ? 4 : 8;  // r01i sweep, whole forward: 4 warps 366, 8 warps 381 TFLOP/s
     e = getenv("GQ_CGB"); env_cg = (e && atoi(e) != 0) ? 1 : 0;
+    e = getenv("GQ_PERSIST"); env_persist = (e && atoi(e) != 0) ? 1 : 0;  // experimental persistent kernel (never run in round 1)
     e = getenv("GQ_TMA"); env_tma = (e && atoi(e) == 0) ? 0 : 1;  // r01k: weight tiles by TMA 439 vs 414 TFLOP/s whole forward
   }
   ConvCfg c;
@@ -733,7 +885,7 @@ static ConvCfg conv_cfg(int Cout) {
   if (env_bn != 128 && Cout % 256 == 0) c.bn = 256;
   c.nst = env_st == 4 ? 4 : 3;
   c.kernel = env_k == 1 ? 1 : 2;
-  c.npw = env_npw; c.cg = env_cg; c.tma = env_tma;
+  c.npw = env_npw; c.cg = env_cg; c.tma = env_tma; c.persist = env_persist;
   if (c.kernel == 2) c.nst = 3;  // the second kernel is built with 3 stages only (4 measured slower, profiles/r01i_qnet_sweep.txt)
   return c;
 }
@@ -775,6 +927,25 @@ static int launch_conv(const ConvCfg& c, dim3 grid, cudaStream_t st, const bf16*
     static bool told = false;
     if (!told) { told = true; fprintf(stderr, "grasp_qnet: %s; weight tiles fall back to cp.async\n", q_err); }
     tma = false;
+  }
+  if (c.persist && tma) {
+    // experimental: one CTA per SM, static tile list, 192 KB of stages (4 / 6 / 8 at BLOCK_N 256 / 128 / 64)
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int gx = (int)grid.x, gy = (int)grid.y, ntiles = gx * gy * (int)grid.z;
+    const int nctas = ntiles < sms ? ntiles : sms;
+#define LAUNCH_P(BN_, ST_)                                                                                                           \
+  do {                                                                                                                               \
+    const size_t psmem = (size_t)ST_ * (BM * BK * 2 + BN_ * BK * 2) + 8 * (2 * ST_ + 4) + 16;                                         \
+    QCK(cudaFuncSetAttribute(k_conv_tc_persist<BN_, ST_, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));             \
+    k_conv_tc_persist<BN_, ST_, EPI><<<nctas, 416, psmem, st>>>(tm, x, bias, y, partials, resid, ss, out, H, W, Cin, Cout, ks, gx, gy, ntiles); \
+  } while (0)
+    if (c.bn == 256) LAUNCH_P(256, 4);
+    else if (c.bn == 128) LAUNCH_P(128, 6);
+    else LAUNCH_P(64, 8);
+#undef LAUNCH_P
+    return 0;
   }
 #define LAUNCH_ONE(BN_, NPW_, TMA_)                                                                                                  \
   do {                                                                                                                               \
