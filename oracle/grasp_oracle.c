@@ -1168,9 +1168,16 @@ static double nt_update(Env* e, const double* jar) { /* forces, active flags, co
   }
   return cost;
 }
+/* solver statistics (profiling aid for the GPU kernel work, read with orc_newton_stats):
+ * [0] solves with constraints, [1] Hessian builds (= Newton iterations that factorise), [2] builds whose active set equals the one of the
+ * previous build of the same solve (H unchanged: the factor could be reused), [3] line-search iterations, [4] constraint rows summed over
+ * solves, [5] solves that ended after one build, [6] after two, [7] after three or more */
+static long g_nt_stats[8];
+void orc_newton_stats(long* out, int reset) { memcpy(out, g_nt_stats, sizeof g_nt_stats); if (reset) memset(g_nt_stats, 0, sizeof g_nt_stats); }
 static void solve_newton(Env* e) {
   const Model* m = e->m;
   int nv = m->nv, n = e->nefc;
+  unsigned char prev_active[4096]; int have_prev = 0, builds = 0;
   memcpy(e->qacc, e->qacc_smooth, sizeof(double) * nv);
   memset(e->qfrc_constraint, 0, sizeof(double) * nv);
   e->solver_iter = 0;
@@ -1207,6 +1214,12 @@ static void solve_newton(Env* e) {
     double gn = 0;
     for (int d = 0; d < nv; d++) { grad[d] = Ma[d] - e->qfrc_smooth[d] - e->qfrc_constraint[d]; gn += grad[d] * grad[d]; }
     if (it > 0 && scale * sqrt(gn) < m->tolerance) break;
+    if (n <= 4096) {
+      if (have_prev) { int same = 1; for (int r = 0; r < n; r++) if (prev_active[r] != (unsigned char)e->nt_active[r]) { same = 0; break; } g_nt_stats[2] += same; }
+      for (int r = 0; r < n; r++) prev_active[r] = (unsigned char)e->nt_active[r];
+      have_prev = 1;
+    }
+    g_nt_stats[1]++; builds++;
     /* H = M + J^T D_active J */
     memset(H, 0, sizeof(double) * nv * nv);
     for (int i = 0; i < nv; i++) {
@@ -1255,6 +1268,7 @@ static void solve_newton(Env* e) {
     if (gtol < ORC_MINVAL) gtol = ORC_MINVAL;
     double alpha = 0, lo = 0, hi = -1;
     for (int ls = 0; ls < 50; ls++) {
+      g_nt_stats[3]++;
       double d1 = g1 + 2 * g2 * alpha, d2 = 2 * g2;
       for (int i = 0; i < n; i++) {
         double x = jar[i] + alpha * jv[i];
@@ -1277,6 +1291,7 @@ static void solve_newton(Env* e) {
     cost = gauss + cost_c;
     if (scale * (oldcost - cost) < m->tolerance) break;
   }
+  g_nt_stats[0]++; g_nt_stats[4] += n; g_nt_stats[builds <= 1 ? 5 : (builds == 2 ? 6 : 7)]++;
 }
 static void solve_constraints(Env* e) { if (e->solver == 1) solve_pgs(e); else solve_newton(e); }
 

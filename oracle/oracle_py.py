@@ -57,12 +57,22 @@ def lib():
         L.orc_depth_2_meters.restype = C.c_double
         L.orc_depth_2_meters.argtypes = [P, C.c_double]
         L.orc_render.argtypes = [P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_float)]
+        L.orc_newton_stats.argtypes = [C.POINTER(C.c_long), C.c_int]
         _LIB = L
     return _LIB
 
 
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def newton_stats(reset=True):
+    """process-wide solver statistics of the oracle (profiling aid): dict with solves, Hessian builds, builds whose active set did not
+    change since the previous build of the same solve, line-search iterations, constraint rows, solves ending after 1 / 2 / 3+ builds"""
+    out = (C.c_long * 8)()
+    lib().orc_newton_stats(out, 1 if reset else 0)
+    keys = ["solves", "builds", "builds_same_active_set", "linesearch_iterations", "rows", "solves_1_build", "solves_2_builds", "solves_3plus_builds"]
+    return dict(zip(keys, [int(v) for v in out]))
 
 
 class OracleEnv:

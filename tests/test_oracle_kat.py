@@ -205,3 +205,24 @@ def test_grasp_attempt_runs_and_is_deterministic(scene_a):
     assert out[0][0] == out[1][0] == 1  # the 4 cm box is picked and carried to the drop bin
     assert out[0][1] == out[1][1] and np.array_equal(out[0][2], out[1][2])
     assert out[0][1][1] in range(200, 500)  # pre-grasp phase length in the range media/console.png shows (362)
+
+
+def test_newton_converges_in_about_one_iteration_with_warm_start(scene_a):
+    """solver statistics over one whole grasp attempt (what the GPU kernel work is planned against): with
+    qacc_warmstart the primal Newton solver needs one Hessian factorisation in > 85 % of the sub-steps and the active set always
+    changes between two factorisations of one solve (so there is nothing to reuse inside a solve)"""
+    from oracle.oracle_py import OracleEnv, newton_stats
+
+    blob, A, _ = scene_a
+    o = OracleEnv(blob)
+    o.reset(reset_qpos_scene_a(A, 3))
+    o.stay(1000)
+    newton_stats()
+    p = object_positions(A, o.qpos)[0]
+    o.move_and_grasp([p[0], p[1], p[2] + 0.02], 0, 0.91)
+    s = newton_stats()
+    o.close()
+    assert s["solves"] > 1000 and s["builds"] / s["solves"] < 1.5
+    assert s["solves_1_build"] / s["solves"] > 0.85
+    assert s["builds_same_active_set"] <= 0.02 * s["builds"]
+    assert 1.0 <= s["linesearch_iterations"] / s["builds"] < 6.0
