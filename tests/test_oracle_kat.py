@@ -226,3 +226,27 @@ def test_newton_converges_in_about_one_iteration_with_warm_start(scene_a):
     assert s["solves_1_build"] / s["solves"] > 0.85
     assert s["builds_same_active_set"] <= 0.02 * s["builds"]
     assert 1.0 <= s["linesearch_iterations"] / s["builds"] < 6.0
+
+
+def test_render_statistics_match_the_reference_mean_and_std(scene_a):
+    """the reference's pickled `mean_and_std` (normalize.py over 100 resets of real MuJoCo renders) holds the depth mean
+    1.5318247 m and std 0.4265042 m of the 200x200 top-down observation (float32 => taken after depth_2_meters) and the RGB means
+    108.3 / 120.3 / 132.3.  The oracle's ray-cast observation of the 6-object scene reproduces the depth statistics to 1e-3 (camera pose,
+    fovy, table extent and depth conversion all enter); colour is flat-shaded here, so the RGB means are only required within 15 %"""
+    from oracle.oracle_py import OracleEnv
+
+    blob, A, _ = scene_a
+    cam = int(np.asarray(A["cam_top_down"]).ravel()[0])
+    depth, rgb = [], []
+    for i in range(6):
+        o = OracleEnv(blob)
+        o.reset(reset_qpos_scene_a(A, i))
+        o.stay(1000)
+        r, d = o.render(cam, 200, 200)
+        depth.append(d); rgb.append(r)
+        o.close()
+    depth, rgb = np.stack(depth).astype(np.float64), np.stack(rgb).astype(np.float64)
+    assert abs(depth.mean() - 1.5318247) < 2e-3, depth.mean()
+    assert abs(depth.std() - 0.4265042) < 2e-3, depth.std()
+    ref_rgb = np.array([108.29777875, 120.32914675, 132.30339475])
+    assert (np.abs(rgb.mean(axis=(0, 1, 2)) / ref_rgb - 1) < 0.15).all(), rgb.mean(axis=(0, 1, 2))
