@@ -418,6 +418,58 @@ __global__ void __launch_bounds__(32 * (NPW + 1)) k_conv_tc(const __grid_constan
   __syncthreads();
   if (warp == 0) tmem_dealloc(tacc, BLOCK_N);
 }
+// epilogue of one 128 x BLOCK_N accumulator (TMEM columns tcol .. tcol + BLOCK_N - 1) for the warp owning lane quarter `quarter`:
+// the same arithmetic as the epilogue of k_conv_tc (shared by the two experimental persistent kernels)
+template <int BLOCK_N, int EPI>
+__device__ __forceinline__ void conv_epilogue_tile(uint32_t tcol, int quarter, int lane, int mt, int n0, int b, int gx, int HW, int Cout,
+                                                   const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ stats,
+                                                   const float* __restrict__ resid, const float2* __restrict__ scale_shift, bf16* __restrict__ out) {
+  const int m = mt * BM + quarter * 32 + lane;
+  const bool mvalid = m < HW;
+  const size_t rowoff = ((size_t)b * HW + m) * Cout + n0;
+  for (int cb = 0; cb < BLOCK_N; cb += 32) {
+    float v[32];
+    tmem_ld32(tcol + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cb, v);
+    if (bias) {
+      const float4* b4 = (const float4*)(bias + n0 + cb);
+#pragma unroll
+      for (int j = 0; j < 8; j++) { const float4 bv = __ldg(b4 + j); v[4 * j] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w; }
+    }
+    if constexpr (EPI == 0) {
+      if (mvalid) {
+        float4* dst = (float4*)(y + rowoff + cb);
+#pragma unroll
+        for (int j = 0; j < 8; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      if (stats) {
+        float q[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) { v[j] = mvalid ? v[j] : 0.f; q[j] = v[j] * v[j]; }
+        const float s1 = warp_colsum32(v, lane), s2 = warp_colsum32(q, lane);
+        float2* pp = (float2*)(stats + ((((size_t)b * gx + mt) * 4 + quarter) * Cout + n0 + cb) * 2);
+        pp[lane] = make_float2(s1, s2);
+      }
+    } else {
+      if (mvalid) {
+        const float4* r4 = (const float4*)(resid + rowoff + cb);
+        const float4* ss4 = (const float4*)(scale_shift + (size_t)b * Cout + n0 + cb);
+        __nv_bfloat162 o[16];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float4 r = __ldg(r4 + j);
+          const float4 sa = __ldg(ss4 + 2 * j), sb = __ldg(ss4 + 2 * j + 1);
+          const float o0 = fmaxf(r.x * sa.x + sa.y + v[4 * j], 0.f), o1 = fmaxf(r.y * sa.z + sa.w + v[4 * j + 1], 0.f);
+          const float o2 = fmaxf(r.z * sb.x + sb.y + v[4 * j + 2], 0.f), o3 = fmaxf(r.w * sb.z + sb.w + v[4 * j + 3], 0.f);
+          o[2 * j] = __floats2bfloat162_rn(o0, o1); o[2 * j + 1] = __floats2bfloat162_rn(o2, o3);
+        }
+        uint4* dst = (uint4*)(out + rowoff + cb);
+#pragma unroll
+        for (int j = 0; j < 4; j++) dst[j] = ((const uint4*)o)[j];
+      }
+    }
+  }
+}
+
 // ---- EXPERIMENTAL (GQ_PERSIST=1, default off; written after the GPU budget of round 1 was spent: compiled, never run — the first thing
 // to test in round 2).  Persistent form of k_conv_tc: one CTA per SM walks a static round-robin list of (m tile, n tile, image) tiles,
 // the accumulator is double-buffered in TMEM (2 x BLOCK_N columns) and the epilogue has its own 4 warps, so the TMEM read-out, the stores
@@ -513,54 +565,109 @@ __global__ void __launch_bounds__(416) k_conv_tc_persist(const __grid_constant__
     int i = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
       const int mt = t % gx, nt = (t / gx) % gy, b = t / (gx * gy);
-      const int m0 = mt * BM, n0 = nt * BLOCK_N, a = i & 1;
+      const int a = i & 1;
       mbar_wait(&acc_full[a], (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
-      const int m = m0 + quarter * 32 + lane;
-      const bool mvalid = m < HW;
-      const size_t rowoff = ((size_t)b * HW + m) * Cout + n0;
-      for (int cb = 0; cb < BLOCK_N; cb += 32) {
-        float v[32];
-        tmem_ld32(tacc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * BLOCK_N + cb), v);
-        if (bias) {
-          const float4* b4 = (const float4*)(bias + n0 + cb);
-#pragma unroll
-          for (int j = 0; j < 8; j++) { const float4 bv = __ldg(b4 + j); v[4 * j] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w; }
-        }
-        if constexpr (EPI == 0) {
-          if (mvalid) {
-            float4* dst = (float4*)(y + rowoff + cb);
-#pragma unroll
-            for (int j = 0; j < 8; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (stats) {
-            float q[32];
-#pragma unroll
-            for (int j = 0; j < 32; j++) { v[j] = mvalid ? v[j] : 0.f; q[j] = v[j] * v[j]; }
-            const float s1 = warp_colsum32(v, lane), s2 = warp_colsum32(q, lane);
-            float2* pp = (float2*)(stats + ((((size_t)b * gx + mt) * 4 + quarter) * Cout + n0 + cb) * 2);
-            pp[lane] = make_float2(s1, s2);
-          }
-        } else {
-          if (mvalid) {
-            const float4* r4 = (const float4*)(resid + rowoff + cb);
-            const float4* ss4 = (const float4*)(scale_shift + (size_t)b * Cout + n0 + cb);
-            __nv_bfloat162 o[16];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-              const float4 r = __ldg(r4 + j);
-              const float4 sa = __ldg(ss4 + 2 * j), sb = __ldg(ss4 + 2 * j + 1);
-              const float o0 = fmaxf(r.x * sa.x + sa.y + v[4 * j], 0.f), o1 = fmaxf(r.y * sa.z + sa.w + v[4 * j + 1], 0.f);
-              const float o2 = fmaxf(r.z * sb.x + sb.y + v[4 * j + 2], 0.f), o3 = fmaxf(r.w * sb.z + sb.w + v[4 * j + 3], 0.f);
-              o[2 * j] = __floats2bfloat162_rn(o0, o1); o[2 * j + 1] = __floats2bfloat162_rn(o2, o3);
-            }
-            uint4* dst = (uint4*)(out + rowoff + cb);
-#pragma unroll
-            for (int j = 0; j < 4; j++) dst[j] = ((const uint4*)o)[j];
-          }
+      conv_epilogue_tile<BLOCK_N, EPI>(tacc + (uint32_t)(a * BLOCK_N), quarter, lane, mt, nt * BLOCK_N, b, gx, HW, Cout, bias, y, stats, resid, scale_shift, out);
+      tc_fence_before();  // the tcgen05.ld of this buffer are complete (wait::ld inside tmem_ld32): hand it back to the MMA warp
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[a])) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tacc, 2 * BLOCK_N);
+}
+
+// ---- EXPERIMENTAL (GQ_PERSIST=2, default off, compiled but never run in round 1): the persistent kernel fed by TMA only.  The
+// activation operand is an **im2col-mode** tensor map over x [N][H][W][C] (cuTensorMapEncodeIm2col: pixel box corners (-pad, -pad) /
+// (pad - (ks - 1), ...), 64 channels per pixel, 128 pixels per column, 128-byte swizzle): one
+// `cp.async.bulk.tensor.4d...im2col` per k-step loads the 128 consecutive output positions of the tile for filter tap (offset_w, offset_h)
+// with hardware zero fill at the image border - the same [128 pixels x 64 channels] swizzled tile the cp.async gather builds (semantics
+// as used by CUTLASS' sm100 implicit-GEMM collective: start coordinate = first output pixel + lower corner, tap passed as offsets).
+// One thread issues both TMAs of a k-step after a single arrive.expect_tx(A + B bytes) on the stage's full barrier (count 1).
+// Roles: warp 0 lane 0 producer, warp 1 lane 0 MMA issuer, warps 2-5 epilogue (lane quarter warp % 4).
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst_smem_addr, const CUtensorMap* tmap, int c, int w, int h, int n, uint16_t off_w,
+                                                   uint16_t off_h, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+               ::"r"(dst_smem_addr), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
+template <int BLOCK_N, int STAGES, int EPI>
+__global__ void __launch_bounds__(192) k_conv_tc_tma(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
+                                                     const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ stats,
+                                                     const float* __restrict__ resid, const float2* __restrict__ scale_shift, bf16* __restrict__ out,
+                                                     int H, int W, int Cin, int Cout, int ks, int gx, int gy, int ntiles) {
+  constexpr int A_STAGE = BM * BK * 2, B_STAGE = BLOCK_N * BK * 2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE;
+  uint64_t* full = (uint64_t*)(smem + STAGES * (A_STAGE + B_STAGE));
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HW = H * W, pad = ks / 2, taps = ks * ks, kchunks = Cin / BK, nk = taps * kchunks;
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 2 * BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tacc = *tmem_slot;
+  constexpr uint32_t idesc = make_idesc(BM, BLOCK_N);
+  if (warp == 0) {
+    if (lane == 0) {
+      int sn = 0, round = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int mt = t % gx, nt = (t / gx) % gy, b = t / (gx * gy);
+        const int m0 = mt * BM, n0 = nt * BLOCK_N;
+        const int oh0 = m0 / W, ow0 = m0 - oh0 * W;
+        int tap = 0, kc = 0;
+        for (int kn = 0; kn < nk; kn++) {
+          if (round > 0) mbar_wait(&empty[sn], (uint32_t)(round - 1) & 1u);
+          mbar_arrive_expect_tx(&full[sn], (uint32_t)(A_STAGE + B_STAGE));
+          tma_load_im2col_4d(smem_u32(sA) + (uint32_t)(sn * A_STAGE), &tmap_x, kc * BK, ow0 - pad, oh0 - pad, b, (uint16_t)(tap % ks), (uint16_t)(tap / ks),
+                             &full[sn]);
+          tma_load_2d(smem_u32(sB) + (uint32_t)(sn * B_STAGE), &tmap_w, kn * BK, n0, &full[sn]);
+          if (++sn == STAGES) { sn = 0; round++; }
+          if (++kc == kchunks) { kc = 0; tap++; }
         }
       }
-      tc_fence_before();  // the tcgen05.ld of this buffer are complete (wait::ld inside tmem_ld32): hand it back to the MMA warp
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0; int i = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
+        const int a = i & 1;
+        mbar_wait(&acc_empty[a], (uint32_t)((i >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t dacc = tacc + (uint32_t)(a * BLOCK_N);
+        for (int kb = 0; kb < nk; kb++) {
+          mbar_wait(&full[s], ph);  // both operands arrive through the async proxy (TMA): no generic-proxy fence needed
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + s * A_STAGE), b_base = smem_u32(sB + s * B_STAGE);
+#pragma unroll
+          for (int k = 0; k < BK / 16; k++)
+            umma_bf16(dacc, make_smem_desc_sw128(a_base + k * 32), make_smem_desc_sw128(b_base + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty[s]);
+          if (kb == nk - 1) umma_commit(&acc_full[a]);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    int i = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
+      const int mt = t % gx, nt = (t / gx) % gy, b = t / (gx * gy);
+      const int a = i & 1;
+      mbar_wait(&acc_full[a], (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      conv_epilogue_tile<BLOCK_N, EPI>(tacc + (uint32_t)(a * BLOCK_N), quarter, lane, mt, nt * BLOCK_N, b, gx, HW, Cout, bias, y, stats, resid, scale_shift, out);
+      tc_fence_before();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[a])) : "memory");
     }
   }
@@ -877,7 +984,7 @@ static ConvCfg conv_cfg(int Cout) {
     e = getenv("GQ_KERNEL"); env_k = e ? atoi(e) : 2;
     e = getenv("GQ_NPW"); env_npw = (e && atoi(e) == 4) ? 4 : 8;  // r01i sweep, whole forward: 4 warps 366, 8 warps 381 TFLOP/s
     e = getenv("GQ_CGB"); env_cg = (e && atoi(e) != 0) ? 1 : 0;
-    e = getenv("GQ_PERSIST"); env_persist = (e && atoi(e) != 0) ? 1 : 0;  // experimental persistent kernel (never run in round 1)
+    e = getenv("GQ_PERSIST"); env_persist = e ? atoi(e) : 0;  // experimental persistent kernels (never run in round 1): 1 cp.async + TMA, 2 TMA only
     e = getenv("GQ_TMA"); env_tma = (e && atoi(e) == 0) ? 0 : 1;  // r01k: weight tiles by TMA 439 vs 414 TFLOP/s whole forward
   }
   ConvCfg c;
@@ -915,6 +1022,31 @@ static int make_weight_tmap(CUtensorMap* m, const void* w, int Cout, int K, int 
   return 0;
 }
 
+// im2col-mode tensor map of the activations x [N][H][W][C] bf16: 64 channels x 128 output positions per load, zero fill outside the image
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                   cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+static int make_act_tmap_im2col(CUtensorMap* m, const void* x, int B, int H, int W, int C, int ks) {
+  static EncodeIm2colFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) fn = (EncodeIm2colFn)p;
+  }
+  if (!fn) { snprintf(q_err, sizeof q_err, "cuTensorMapEncodeIm2col is not available"); return -3; }
+  const int pad = ks / 2;
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  int lower[2] = {-pad, -pad}, upper[2] = {pad - (ks - 1), pad - (ks - 1)};  // fprop corners (W, H): as many box positions as output pixels
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstride, lower, upper, (cuuint32_t)BK, (cuuint32_t)BM, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(q_err, sizeof q_err, "cuTensorMapEncodeIm2col failed (%d)", (int)r); return -3; }
+  return 0;
+}
+
 // EPI 0: y (+ BN partials); EPI 1: out = relu(resid * scale + shift + conv + bias) bf16
 template <int EPI>
 static int launch_conv(const ConvCfg& c, dim3 grid, cudaStream_t st, const bf16* x, const bf16* w, const float* bias, float* y, float* partials,
@@ -941,6 +1073,21 @@ static int launch_conv(const ConvCfg& c, dim3 grid, cudaStream_t st, const bf16*
     QCK(cudaFuncSetAttribute(k_conv_tc_persist<BN_, ST_, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));             \
     k_conv_tc_persist<BN_, ST_, EPI><<<nctas, 416, psmem, st>>>(tm, x, bias, y, partials, resid, ss, out, H, W, Cin, Cout, ks, gx, gy, ntiles); \
   } while (0)
+    if (c.persist == 2) {
+      alignas(64) CUtensorMap tmx;
+      if (make_act_tmap_im2col(&tmx, x, (int)grid.z, H, W, Cin, ks)) return -3;
+#define LAUNCH_T(BN_, ST_)                                                                                                           \
+  do {                                                                                                                               \
+    const size_t psmem = (size_t)ST_ * (BM * BK * 2 + BN_ * BK * 2) + 8 * (2 * ST_ + 4) + 16;                                         \
+    QCK(cudaFuncSetAttribute(k_conv_tc_tma<BN_, ST_, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));                 \
+    k_conv_tc_tma<BN_, ST_, EPI><<<nctas, 192, psmem, st>>>(tm, tmx, bias, y, partials, resid, ss, out, H, W, Cin, Cout, ks, gx, gy, ntiles); \
+  } while (0)
+      if (c.bn == 256) LAUNCH_T(256, 4);
+      else if (c.bn == 128) LAUNCH_T(128, 6);
+      else LAUNCH_T(64, 8);
+#undef LAUNCH_T
+      return 0;
+    }
     if (c.bn == 256) LAUNCH_P(256, 4);
     else if (c.bn == 128) LAUNCH_P(128, 6);
     else LAUNCH_P(64, 8);

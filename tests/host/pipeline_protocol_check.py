@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Model check of the mbarrier protocol of the persistent convolution kernel (k_conv_tc_persist in csrc/qnet.cu), which was written
-after the GPU budget of round 1 was spent and has not run on a GPU yet.
+"""Model check of the mbarrier protocol of the persistent convolution kernels (k_conv_tc_persist and, with tma_only, k_conv_tc_tma in
+csrc/qnet.cu), which were written after the GPU budget of round 1 was spent and have not run on a GPU yet.
 
 The kernel's control flow is restated with the SAME index / parity expressions (stage = it % STAGES with a running round counter,
 producer waits empty[s] with parity (round - 1) & 1, the MMA issuer waits full[s] with a phase bit that flips when s wraps, accumulator
@@ -49,9 +49,12 @@ class Bar:
         return parity != (self.phase & 1)
 
 
-def simulate(seed, stages, nk, ntiles, nprod=3, nepi=2, b_bytes=64):
+def simulate(seed, stages, nk, ntiles, nprod=3, nepi=2, b_bytes=64, tma_only=False):
+    """tma_only: k_conv_tc_tma (GQ_PERSIST=2) - one producer thread, both operands by TMA, full barrier count 1 + transaction bytes"""
     rng = random.Random(seed)
-    full = [Bar(nprod + 1) for _ in range(stages)]
+    if tma_only:
+        nprod = 1
+    full = [Bar(1 if tma_only else nprod + 1) for _ in range(stages)]
     empty = [Bar(1) for _ in range(stages)]
     acc_full = [Bar(1) for _ in range(2)]
     acc_empty = [Bar(nepi) for _ in range(2)]
@@ -82,15 +85,24 @@ def simulate(seed, stages, nk, ntiles, nprod=3, nepi=2, b_bytes=64):
                     w = stage_fill[s].setdefault((tt, kk), set())
                     w.add(("A", who))
                     full[s].arrive()
-                if pid == 0:
-                    full[sn].expect_tx_arrive(b_bytes)
+                if tma_only:
+                    full[sn].expect_tx_arrive(2 * b_bytes)
 
+                    def tma_a(s=s_, tt=t_, kk=k_):
+                        assert stage_reads_done[s], "stage %d (activations) overwritten before its MMAs completed" % s
+                        stage_fill[s].setdefault((tt, kk), set()).add(("A", 0))
+                        full[s].complete_tx(b_bytes)
+                    defer("tma", tma_a)
+                elif pid == 0:
+                    full[sn].expect_tx_arrive(b_bytes)
+                if pid == 0:
                     def tma(s=s_, tt=t_, kk=k_):
                         assert stage_reads_done[s], "stage %d (weights) overwritten before its MMAs completed" % s
                         stage_fill[s].setdefault((tt, kk), set()).add(("B", 0))
                         full[s].complete_tx(b_bytes)
                     defer("tma", tma)
-                defer("cpasync%d" % pid, land)
+                if not tma_only:
+                    defer("cpasync%d" % pid, land)
                 yield ("step",)
                 sn += 1
                 if sn == stages:
@@ -188,7 +200,8 @@ def main():
     for r in range(n):
         rr = random.Random(r)
         simulate(r, rr.choice((3, 4, 6, 8)), rr.choice((1, 4, 9, 18, 36)), rr.choice((1, 2, 4, 7, 9)), nprod=rr.choice((1, 2, 4)), nepi=rr.choice((1, 2, 4)))
-        cases += 1
+        simulate(r, rr.choice((3, 4, 6, 8)), rr.choice((1, 4, 9, 18, 36)), rr.choice((1, 2, 4, 7, 9)), nepi=rr.choice((1, 2, 4)), tma_only=True)
+        cases += 2
     print("pipeline protocol: %d randomised schedules, no deadlock, no aliasing, no hazard" % cases)
 
 
