@@ -19,11 +19,12 @@ def build():
 def lib():
     global _LIB
     if _LIB is None:
-        so = os.environ.get("GRASP_ORACLE_SO") or os.path.join(_DIR, "libgrasp_oracle.so")  # override: rounding-sensitivity experiments
-        if os.environ.get("GRASP_ORACLE_SO"):
-            pass
-        elif not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(_DIR, "grasp_oracle.c")):
-            build()
+        # GRASP_ORACLE_SO: another build of the same source (e.g. -ffp-contract=fast) for rounding-sensitivity experiments
+        so = os.environ.get("GRASP_ORACLE_SO")
+        if not so:
+            so = os.path.join(_DIR, "libgrasp_oracle.so")
+            if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(_DIR, "grasp_oracle.c")):
+                build()
         L = C.CDLL(so)
         P, D, I = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
         L.orc_model_load.restype = P
