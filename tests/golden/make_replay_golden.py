@@ -54,9 +54,11 @@ def choose_action(rng, depth):
     return [y * W + x, int(rng.randint(0, 6))]
 
 
-def replay_env(i, actions=None, states=None):
+def replay_env(i, actions=None, states=None, perturb_ulp=0):
     """Runs env i on the oracle.  `actions` given: replay them; None: choose them from the oracle's own observations.
-    `states` given ((qpos [T,nq], qvel [T,nv])): every step starts from the stored state instead of the oracle's own."""
+    `states` given ((qpos [T,nq], qvel [T,nv])): every step starts from the stored state instead of the oracle's own.
+    `perturb_ulp`: move the x coordinate of the first object by one unit in the last place after the settle (rounding-
+    sensitivity experiment of tools/free_run_replay.py; 0 for the fixture)."""
     from mujoco_rl_ur5_b200.model.scene import load_scene, load_scene_blob
     from oracle.oracle_py import OracleEnv
     from tests.common import reset_qpos_scene_a
@@ -67,6 +69,8 @@ def replay_env(i, actions=None, states=None):
     o = OracleEnv(blob)
     o.reset(reset_qpos_scene_a(A, i))
     o.stay(1000)
+    if perturb_ulp:
+        o.qpos[8] = np.nextafter(o.qpos[8], np.inf if perturb_ulp > 0 else -np.inf)
     rng = np.random.RandomState(30000 + i)
     rec = []
     for k in range(N_STEPS):
