@@ -94,6 +94,15 @@ int ge_get_status(ge_handle h, int32_t* status /*[N] dev*/);
 /* busy [N] u8 [dev]: 1 while the env still has a movement or program pending (i.e. ge_run would advance it) */
 int ge_get_busy(ge_handle h, uint8_t* busy);
 
+/* MJ_Controller.actuate_joint_group (MujocoController.py:256-267) writes sim.data.ctrl; ge_set_ctrl is that write for all 7
+ * actuators: ctrl [N,7] f64 [dev], env_mask [N] u8 [dev] or NULL.  ge_get_ctrl reads sim.data.ctrl back ([N,7] [dev]): after a
+ * movement it holds the last PID outputs (MujocoController.py:327). */
+int ge_set_ctrl(ge_handle h, const double* ctrl, const uint8_t* env_mask);
+int ge_get_ctrl(ge_handle h, double* ctrl);
+/* `substeps` bare sim.step() calls (MujocoController.py:379, :611) with the controls as they stand - no PID evaluation, no
+ * movement bookkeeping: the open-loop counterpart of ge_run for callers that drive sim.data.ctrl themselves. */
+int ge_step_open_loop(ge_handle h, int substeps, const uint8_t* env_mask);
+
 /* MJ_Controller.ik (MujocoController.py:467-517): xyz [N,3] -> q5 [N,5], ok [N] u8 (all [dev]) */
 int ge_ik(ge_handle h, const double* xyz, double* q5, uint8_t* ok);
 /* MJ_Controller.pixel_2_world (MujocoController.py:783-806): pixel_x, pixel_y [N] int32, depth [N] f32 -> xyz [N,3] f64 */

@@ -35,14 +35,39 @@ class BatchedGreedyAgent:
         act, val = self.qnet.greedy(self.q_values(obs))
         return act.to(self.torch.int32), val
 
+    def random_table_actions(self, obs, max_rounds=64):
+        """The reference's random action (Grasping_Agent_multidiscrete.py:262-279): draw a flat action uniformly from all
+        W*H*n_rot, look the pixel's depth up in the current observation, transform it with pixel_2_world and REJECT it unless the
+        point lies on or above the table (z >= TABLE_HEIGHT - 0.01); resample until accepted.  Batched: every round redraws only the
+        environments that are still rejected (pixel_2_world is the engine's kernel).  Returns int32 [N,2] on the device."""
+        t = self.torch
+        env = self.env
+        N, W, H, R = env.n_envs, env.IMAGE_WIDTH, env.IMAGE_HEIGHT, len(env.rotations)
+        dev = obs["depth"].device
+        out = t.zeros((N, 2), dtype=t.int32, device=dev)
+        todo = t.ones(N, dtype=t.bool, device=dev)
+        ar = t.arange(N, device=dev)
+        for _ in range(max_rounds):
+            flat = t.randint(0, W * H * R, (N,), generator=self.gen, device=dev)
+            a1, a2 = flat % (W * H), flat // (W * H)
+            x, y = a1 % W, a1 // W
+            d = obs["depth"][ar, y, x].contiguous()
+            xyz = env.engine.pixel_2_world(x.to(t.int32).contiguous(), y.to(t.int32).contiguous(), d, env.cam, W, H)
+            ok = todo & (xyz[:, 2] >= env.TABLE_HEIGHT - 0.01)
+            out[ok, 0] = a1[ok].to(t.int32)
+            out[ok, 1] = a2[ok].to(t.int32)
+            todo = todo & ~ok
+            if not bool(todo.any()):
+                break
+        if bool(todo.any()):  # an image without a single table pixel: keep the last draw (the reference would loop forever)
+            out[todo, 0] = a1[todo].to(t.int32)
+            out[todo, 1] = a2[todo].to(t.int32)
+        return out
+
     def epsilon_greedy(self, obs, eps):
-        """with probability eps a uniformly random (pixel, rotation) — the reference additionally rejects pixels off the table by
-        looking up the depth (Grasping_Agent_multidiscrete.py:262-279); here random pixels are drawn inside the table's image box"""
+        """with probability eps the reference's depth-filtered random action (random_table_actions), else the greedy one"""
         t = self.torch
         act, val = self.greedy(obs)
-        N, W = act.shape[0], self.env.IMAGE_WIDTH
-        px = t.randint(40, 160, (N,), generator=self.gen, device=act.device)
-        py = t.randint(60, 140, (N,), generator=self.gen, device=act.device)
-        rnd = t.stack([py * W + px, t.randint(0, len(self.env.rotations), (N,), generator=self.gen, device=act.device)], dim=1).to(t.int32)
-        pick = t.rand(N, generator=self.gen, device=act.device) < eps
+        rnd = self.random_table_actions(obs)
+        pick = t.rand(act.shape[0], generator=self.gen, device=act.device) < eps
         return t.where(pick[:, None], rnd, act), val

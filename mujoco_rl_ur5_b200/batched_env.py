@@ -94,7 +94,9 @@ class BatchedGraspEnv:
         eng.set_state(q)
         eng.stay(self.settle_ms)
         eng.run()
-        return self.get_observation()
+        # unlike the reference (quirk Q5: GraspEnv.reset leaves current_observation stale) the batched API acts on what it returns
+        self.current_observation = self.get_observation()
+        return self.current_observation
 
     def get_observation(self):
         rgb, depth = self.engine.render(self.cam, self.IMAGE_WIDTH, self.IMAGE_HEIGHT)

@@ -51,9 +51,48 @@ class _PIDProxy:
         self._c.current_target_joint_values[self._i] = v
 
 
+class _CtrlView:
+    """`sim.data.ctrl`: the 7 actuator controls of this environment.  Reads come from the device (after a movement: the last PID
+    outputs, MujocoController.py:327); item assignment is the open-loop write of actuate_joint_group / toss_it_from_the_ellbow
+    (MujocoController.py:256-267, :605-612) and goes straight to the device row."""
+
+    def __init__(self, ctrl):
+        self._c = ctrl
+
+    def _read(self):
+        return self._c.engine.get_ctrl()[self._c.env_index].cpu().numpy()
+
+    def __len__(self):
+        return 7
+
+    def __iter__(self):
+        return iter(self._read())
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._read()
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, k):
+        return self._read()[k]
+
+    def __setitem__(self, k, v):
+        eng, e = self._c.engine, self._c.env_index
+        full = eng.get_ctrl()
+        row = full[e].cpu().numpy()
+        row[k] = v
+        full[e] = eng.torch.as_tensor(row, dtype=full.dtype, device=full.device)
+        mask = np.zeros(eng.n_envs, np.uint8)
+        mask[e] = 1
+        eng.set_ctrl(full, mask)
+
+    def __repr__(self):
+        return repr(self._read())
+
+
 class _Data:
     def __init__(self, ctrl):
         self._c = ctrl
+        self._ctrl = _CtrlView(ctrl)
 
     @property
     def qpos(self):
@@ -65,7 +104,11 @@ class _Data:
 
     @property
     def ctrl(self):
-        return np.zeros(7)
+        return self._ctrl
+
+    @ctrl.setter
+    def ctrl(self, v):
+        self._ctrl[:] = v
 
     @property
     def body_xpos(self):
@@ -78,8 +121,11 @@ class _Sim:
         self._c = ctrl
 
     def step(self):
-        # one PID-free sub-step is not exposed by the reference's callers except toss_it_from_the_ellbow (out of scope)
-        raise NotImplementedError("sim.step() is driven by the device control loop; use move_group_to_joint_target / stay")
+        """mujoco_py MjSim.step(): ONE bare mj_step with sim.data.ctrl as it stands (MujocoController.py:379, :611) - no PID
+        evaluation; the closed loop is move_group_to_joint_target."""
+        mask = np.zeros(self._c.engine.n_envs, np.uint8)
+        mask[self._c.env_index] = 1
+        self._c.engine.step_open_loop(1, mask)
 
     def render(self, width=200, height=200, camera_name="top_down", depth=True):
         rgb, d = self._c.get_image_data(camera=camera_name, width=width, height=height)
@@ -212,7 +258,16 @@ class MJ_Controller(object):
 
     # ------------------------------------------------------------------ movements
     def actuate_joint_group(self, group, motor_values):
-        print("Could not actuate requested joint group.")  # open-loop torques bypass the device control loop (README demo only)
+        """Open-loop write of the group's motor controls (MujocoController.py:256-267); they act in the sim.step() calls that follow
+        and are overwritten by the next PID evaluation of move_group_to_joint_target, as in the reference."""
+        try:
+            assert group in self.groups.keys(), "No group with name {} exists!".format(group)
+            assert len(motor_values) == len(self.groups[group]), "Invalid number of actuator values!"
+            for i, v in enumerate(self.groups[group]):
+                self.sim.data.ctrl[v] = motor_values[i]
+        except Exception as e:
+            print(e)
+            print("Could not actuate requested joint group.")
 
     def move_group_to_joint_target(self, group="All", target=None, tolerance=0.1, max_steps=10000, plot=False, marker=False,
                                    render=True, quiet=False):

@@ -30,6 +30,9 @@ typedef void* vh;
   int ge_get_grasp_info_##suffix(vh, int32_t*);                                                                                    \
   int ge_get_status_##suffix(vh, int32_t*);                                                                                        \
   int ge_get_busy_##suffix(vh, uint8_t*);                                                                                          \
+  int ge_set_ctrl_##suffix(vh, const double*, const uint8_t*);                                                                     \
+  int ge_get_ctrl_##suffix(vh, double*);                                                                                           \
+  int ge_step_open_loop_##suffix(vh, int, const uint8_t*);                                                                         \
   int ge_ik_##suffix(vh, const double*, double*, uint8_t*);                                                                        \
   int ge_pixel_2_world_##suffix(vh, int, int, int, const int32_t*, const int32_t*, const float*, double*);                         \
   int ge_render_##suffix(vh, int, int, int, uint8_t*, float*);                                                                     \
@@ -86,6 +89,9 @@ int ge_get_results(ge_handle h, int32_t* r, int32_t* s, uint8_t* rw, int64_t* t)
 int ge_get_grasp_info(ge_handle h, int32_t* i) { CHECK_H; return FWD(ge_get_grasp_info_smem(h->h, i), ge_get_grasp_info_hbm(h->h, i)); }
 int ge_get_status(ge_handle h, int32_t* s) { CHECK_H; return FWD(ge_get_status_smem(h->h, s), ge_get_status_hbm(h->h, s)); }
 int ge_get_busy(ge_handle h, uint8_t* b) { CHECK_H; return FWD(ge_get_busy_smem(h->h, b), ge_get_busy_hbm(h->h, b)); }
+int ge_set_ctrl(ge_handle h, const double* c, const uint8_t* m) { CHECK_H; return FWD(ge_set_ctrl_smem(h->h, c, m), ge_set_ctrl_hbm(h->h, c, m)); }
+int ge_get_ctrl(ge_handle h, double* c) { CHECK_H; return FWD(ge_get_ctrl_smem(h->h, c), ge_get_ctrl_hbm(h->h, c)); }
+int ge_step_open_loop(ge_handle h, int n, const uint8_t* m) { CHECK_H; return FWD(ge_step_open_loop_smem(h->h, n, m), ge_step_open_loop_hbm(h->h, n, m)); }
 int ge_ik(ge_handle h, const double* x, double* q, uint8_t* ok) { CHECK_H; return FWD(ge_ik_smem(h->h, x, q, ok), ge_ik_hbm(h->h, x, q, ok)); }
 int ge_pixel_2_world(ge_handle h, int cam, int w, int hh, const int32_t* px, const int32_t* py, const float* d, double* xyz) {
   CHECK_H;

@@ -41,6 +41,9 @@
 #define ge_get_grasp_info GE_API(ge_get_grasp_info)
 #define ge_get_status GE_API(ge_get_status)
 #define ge_get_busy GE_API(ge_get_busy)
+#define ge_set_ctrl GE_API(ge_set_ctrl)
+#define ge_get_ctrl GE_API(ge_get_ctrl)
+#define ge_step_open_loop GE_API(ge_step_open_loop)
 #define ge_ik GE_API(ge_ik)
 #define ge_pixel_2_world GE_API(ge_pixel_2_world)
 #define ge_render GE_API(ge_render)

@@ -210,6 +210,37 @@ __global__ void k_targets(EnvArrays E, int n_env, const double* in, double* out)
   if (in) E.ctl[(size_t)env * 32 + CTL_TARGET + a] = in[i];
   if (out) out[i] = E.ctl[(size_t)env * 32 + CTL_TARGET + a];
 }
+// sim.data.ctrl[:] = values (MJ_Controller.actuate_joint_group, MujocoController.py:256-267) / read-back
+__global__ void k_ctrl(EnvArrays E, int n_env, const double* in, double* out, const unsigned char* emask) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_env * GE_NU) return;
+  int env = i / GE_NU, a = i % GE_NU;
+  if (in && !(emask && !emask[env])) E.ctl[(size_t)env * 32 + CTL_CTRL + a] = in[i];
+  if (out) out[i] = E.ctl[(size_t)env * 32 + CTL_CTRL + a];
+}
+// `nsub` bare sim.step() calls with the controls as they stand (no PID evaluation): what a caller of the reference gets from
+// sim.step() after actuate_joint_group (MujocoController.py:256-267, :611).  One warp per CTA; not a throughput path.
+__global__ void __launch_bounds__(32) k_step_open(EnvArrays E, int n_env, int nsub, const unsigned char* emask) {
+  extern __shared__ double smem[];
+  const DevModel& m = c_m; const Layout& L = c_L;
+  int env = blockIdx.x, lane = threadIdx.x;
+  if (env >= n_env || (emask && !emask[env])) return;
+#if GE_WS_IN_HBM
+  double* ws = E.gws + (size_t)env * (L.total_bytes / 8);
+#else
+  double* ws = smem;
+#endif
+  int* wi = (int*)(ws + L.total_doubles);
+  LANE_LOOP(i, m.nq) ws[L.qpos + i] = E.qpos[(size_t)env * m.nq + i];
+  LANE_LOOP(i, m.nv) { ws[L.qvel + i] = E.qvel[(size_t)env * m.nv + i]; ws[L.qaccws + i] = E.qaccws[(size_t)env * m.nv + i]; }
+  ws[L.ctl + lane] = E.ctl[(size_t)env * 32 + lane];
+  __syncwarp();
+  int status = E.status[env];
+  for (int it = 0; it < nsub; it++) sim_step(ws, wi, lane, &status, false);
+  LANE_LOOP(i, m.nq) E.qpos[(size_t)env * m.nq + i] = ws[L.qpos + i];
+  LANE_LOOP(i, m.nv) { E.qvel[(size_t)env * m.nv + i] = ws[L.qvel + i]; E.qaccws[(size_t)env * m.nv + i] = ws[L.qaccws + i]; }
+  if (lane == 0) { E.status[env] = status; E.substeps[env] += nsub; }
+}
 __global__ void k_busy(EnvArrays E, int n_env, unsigned char* busy) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env < n_env) busy[env] = (E.cmd_active[env] || E.prog_phase[env] != PH_NONE) ? 1 : 0;
@@ -442,7 +473,10 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
   h->ws_smem = h->lay.ws_global ? 0 : (size_t)h->lay.total_bytes;
   if (h->ws_smem) {
     CK(cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, h->wpb * h->lay.total_bytes));
-    if (h->lay.total_bytes > 48 * 1024) CK(cudaFuncSetAttribute(k_debug, cudaFuncAttributeMaxDynamicSharedMemorySize, h->lay.total_bytes));
+    if (h->lay.total_bytes > 48 * 1024) {
+      CK(cudaFuncSetAttribute(k_debug, cudaFuncAttributeMaxDynamicSharedMemorySize, h->lay.total_bytes));
+      CK(cudaFuncSetAttribute(k_step_open, cudaFuncAttributeMaxDynamicSharedMemorySize, h->lay.total_bytes));
+    }
   }
   if (h->lay.fk_bytes > 48 * 1024) CK(cudaFuncSetAttribute(k_body_xpos, cudaFuncAttributeMaxDynamicSharedMemorySize, h->lay.fk_bytes));
   EnvArrays& E = h->E;
@@ -636,6 +670,30 @@ extern "C" int ge_get_targets(ge_handle h, double* target) {
   if (bind(h)) return GE_ERR_CUDA;
   k_targets<<<(h->n_envs * GE_NU + 127) / 128, 128, 0, h->stream>>>(h->E, h->n_envs, nullptr, target);
   h->launches++;
+  CK(cudaGetLastError());
+  return GE_OK;
+}
+extern "C" int ge_set_ctrl(ge_handle h, const double* ctrl, const uint8_t* env_mask) {
+  if (!h || !ctrl) return fail(GE_ERR_ARG, "ge_set_ctrl: bad argument");
+  if (bind(h)) return GE_ERR_CUDA;
+  k_ctrl<<<(h->n_envs * GE_NU + 127) / 128, 128, 0, h->stream>>>(h->E, h->n_envs, ctrl, nullptr, env_mask);
+  h->launches++;
+  CK(cudaGetLastError());
+  return GE_OK;
+}
+extern "C" int ge_get_ctrl(ge_handle h, double* ctrl) {
+  if (!h || !ctrl) return fail(GE_ERR_ARG, "ge_get_ctrl: bad argument");
+  if (bind(h)) return GE_ERR_CUDA;
+  k_ctrl<<<(h->n_envs * GE_NU + 127) / 128, 128, 0, h->stream>>>(h->E, h->n_envs, nullptr, ctrl, nullptr);
+  h->launches++;
+  CK(cudaGetLastError());
+  return GE_OK;
+}
+extern "C" int ge_step_open_loop(ge_handle h, int substeps, const uint8_t* env_mask) {
+  if (!h || substeps <= 0) return fail(GE_ERR_ARG, "ge_step_open_loop: bad argument");
+  if (bind(h)) return GE_ERR_CUDA;
+  k_step_open<<<h->n_envs, 32, h->ws_smem, h->stream>>>(h->E, h->n_envs, substeps, env_mask);
+  h->launches++; h->substep_launches++;
   CK(cudaGetLastError());
   return GE_OK;
 }

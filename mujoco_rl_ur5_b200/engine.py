@@ -16,7 +16,7 @@ _LIB = None
 SYMBOLS = [
     "ge_last_error", "ge_version", "ge_create", "ge_destroy", "ge_size", "ge_set_state", "ge_get_state", "ge_get_body_xpos",
     "ge_set_gain", "ge_set_targets", "ge_get_targets", "ge_move_group", "ge_move_ee", "ge_stay", "ge_grasp", "ge_run", "ge_run_async", "ge_get_results",
-    "ge_get_grasp_info", "ge_get_status", "ge_get_busy", "ge_ik", "ge_pixel_2_world", "ge_render", "ge_debug_forward", "ge_counters",
+    "ge_get_grasp_info", "ge_get_status", "ge_get_busy", "ge_set_ctrl", "ge_get_ctrl", "ge_step_open_loop", "ge_ik", "ge_pixel_2_world", "ge_render", "ge_debug_forward", "ge_counters",
 ]
 GROUPS = {"All": 0x7F, "Arm": 0x1F, "Gripper": 0x40}
 MOVE_RESULT = {0: "", 1: "success", 2: "max. steps reached: {}", 3: "No valid joint angles received, could not move EE to position."}
@@ -56,6 +56,9 @@ def load_library():
         L.ge_get_grasp_info.argtypes = [P, P]
         L.ge_get_status.argtypes = [P, P]
         L.ge_get_busy.argtypes = [P, P]
+        L.ge_set_ctrl.argtypes = [P, P, P]
+        L.ge_get_ctrl.argtypes = [P, P]
+        L.ge_step_open_loop.argtypes = [P, C.c_int, P]
         L.ge_ik.argtypes = [P, P, P, P]
         L.ge_pixel_2_world.argtypes = [P, C.c_int, C.c_int, C.c_int, P, P, P, P]
         L.ge_render.argtypes = [P, C.c_int, C.c_int, C.c_int, P, P]
@@ -237,6 +240,26 @@ class BatchedEngine:
         b = t.empty(self.n_envs, dtype=t.uint8, device=self.device)
         self._ck(self.L.ge_get_busy(self.h, _ptr(b)), "ge_get_busy")
         return b
+
+    def set_ctrl(self, ctrl, env_mask=None):
+        """sim.data.ctrl[:] = ctrl for all 7 actuators ([N,7]); the values stay until the next PID evaluation overwrites them"""
+        t = self.torch
+        c = self._dev(ctrl, t.float64).reshape(self.n_envs, 7)
+        env_mask = self._dev(env_mask, t.uint8)
+        self._ck(self.L.ge_set_ctrl(self.h, _ptr(c), _ptr(env_mask)), "ge_set_ctrl")
+        self._keep = (c, env_mask)
+
+    def get_ctrl(self):
+        t = self.torch
+        c = t.empty((self.n_envs, 7), dtype=t.float64, device=self.device)
+        self._ck(self.L.ge_get_ctrl(self.h, _ptr(c)), "ge_get_ctrl")
+        return c
+
+    def step_open_loop(self, substeps=1, env_mask=None):
+        """`substeps` bare sim.step() calls with the current controls (no PID)"""
+        env_mask = self._dev(env_mask, self.torch.uint8)
+        self._ck(self.L.ge_step_open_loop(self.h, int(substeps), _ptr(env_mask)), "ge_step_open_loop")
+        self._keep = env_mask
 
     # ------------------------------------------------------------------ camera / IK
     def ik(self, xyz):

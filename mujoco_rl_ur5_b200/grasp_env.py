@@ -7,8 +7,9 @@ Same constructor keywords, `reset()`, `step(action, record_grasps=False, markers
 `BatchedGraspEnv` for throughput.
 
 Deviations from the reference, all documented in DESIGN.md: deterministic `stay` / PID period, analytic IK
-(A.4), the 6-object scene when no file is given (GRASP_SCENE=B or file=...many_objects.xml selects the reference's default
-40-object scene), no viewer / cv2 windows.
+(A.4), no viewer / cv2 windows.  The default scene is the reference's (`file="/UR5+gripper/UR5gripper_2_finger_many_objects.xml"`,
+GraspingEnv.py:30); `file="/UR5+gripper/UR5gripper_2_finger.xml"` (or GRASP_SCENE=A in the environment, announced on stdout)
+selects the 6-object scene.
 """
 import copy
 import math
@@ -31,17 +32,26 @@ except Exception:  # pragma: no cover - the shim lives in mujoco_rl_ur5_b200/com
     from gym import spaces, utils
 
 
+REFERENCE_DEFAULT_FILE = "/UR5+gripper/UR5gripper_2_finger_many_objects.xml"  # GraspingEnv.py:30
+
+
 def _scene_key(file):
-    if file is None:
-        return os.environ.get("GRASP_SCENE", "A")
+    """(scene key, came from the GRASP_SCENE override?)  The MJCFs are compiled into assets/scene_{a,b}.blob; `file` selects one by
+    name exactly as the reference's argument selects the XML."""
+    if file is None or str(file) == REFERENCE_DEFAULT_FILE:
+        ov = os.environ.get("GRASP_SCENE")
+        if ov in ("A", "B"):
+            return ov, True
+        return "B", False
     name = os.path.basename(str(file))
-    return "B" if "many_objects" in name else "A"
+    return ("B" if "many_objects" in name else "A"), False
 
 
 class GraspEnv(utils.EzPickle):
     metadata = {"render.modes": ["rgb_array"], "video.frames_per_second": 500}
 
-    def __init__(self, file=None, image_width=200, image_height=200, show_obs=True, demo=False, render=False, device=0, quiet=False):
+    def __init__(self, file=REFERENCE_DEFAULT_FILE, image_width=200, image_height=200, show_obs=True, demo=False, render=False, device=0,
+                 quiet=False, strict_reference_quirks=True):
         self.initialized = False
         self.IMAGE_WIDTH = image_width
         self.IMAGE_HEIGHT = image_height
@@ -49,7 +59,11 @@ class GraspEnv(utils.EzPickle):
         self.action_space_type = "multidiscrete"
         self.step_called = 0
         utils.EzPickle.__init__(self)
-        self.scene = _scene_key(file)
+        self.scene, overridden = _scene_key(file)
+        if overridden:
+            print("GraspEnv: GRASP_SCENE={} overrides the reference's default scene ({})".format(self.scene, REFERENCE_DEFAULT_FILE))
+        # reference quirks kept by default (Q5: reset() leaves current_observation stale)
+        self.strict_reference_quirks = bool(strict_reference_quirks)
         self.arrays, self.names = load_scene(self.scene)
         self.engine = BatchedEngine(load_scene_blob(self.scene), 1, device)
         self.model = _Model(self.arrays, self.names)
@@ -228,7 +242,12 @@ class GraspEnv(utils.EzPickle):
         self.controller.stay(1000, render=self.render)
         if self.demo_mode:
             self.controller.stay(5000, render=self.render)
-        return self.get_observation(show=self.show_observations)
+        obs = self.get_observation(show=self.show_observations)
+        if not self.strict_reference_quirks:
+            # the reference does NOT do this (quirk Q5, GraspingEnv.py:87-88,477): the first step of every episode but the first reads
+            # its depth from the previous episode's last image
+            self.current_observation = obs
+        return obs
 
     def set_state(self, qpos, qvel):
         self.engine.set_state(np.asarray(qpos, dtype=np.float64).reshape(1, -1), np.asarray(qvel, dtype=np.float64).reshape(1, -1))

@@ -41,13 +41,13 @@ class Kinematics:
 
     def forward(self, qpos):
         M = self.M
-        nb = int(M["nbody"])
+        nb = int(np.asarray(M["nbody"]).ravel()[0])
         xpos = np.zeros((nb, 3))
         xquat = np.zeros((nb, 4))
         xquat[0] = [1, 0, 0, 0]
         xmat = np.zeros((nb, 3, 3))
         xmat[0] = np.eye(3)
-        nj = int(M["njnt"])
+        nj = int(np.asarray(M["njnt"]).ravel()[0])
         xanchor = np.zeros((nj, 3))
         xaxis = np.zeros((nj, 3))
         for b in range(1, nb):
@@ -81,7 +81,7 @@ class Kinematics:
     def jacobian(self, st, body, point):
         """3 x nv translational (of world `point` attached to `body`) and rotational Jacobians."""
         M = self.M
-        nv = int(M["nv"])
+        nv = int(np.asarray(M["nv"]).ravel()[0])
         Jp, Jr = np.zeros((3, nv)), np.zeros((3, nv))
         d = M["body_lastdof"][body]
         while d >= 0:
@@ -110,10 +110,10 @@ class Kinematics:
 
     def mass_matrix(self, qpos):
         M = self.M
-        nv = int(M["nv"])
+        nv = int(np.asarray(M["nv"]).ravel()[0])
         st = self.forward(qpos)
         H = np.diag(np.asarray(M["dof_armature"], dtype=np.float64).copy()) if nv else np.zeros((0, 0))
-        for b in range(1, int(M["nbody"])):
+        for b in range(1, int(np.asarray(M["nbody"]).ravel()[0])):
             if M["body_lastdof"][b] < 0 or M["body_mass"][b] <= 0:
                 continue
             Jp, Jr = self.jacobian(st, b, st["xipos"][b])

@@ -68,6 +68,17 @@ def save_transitions(path, rgb, depth, actions, rewards):
     return len(d["actions"])
 
 
+def _torch_load(path):
+    """torch.load of a (trusted) data file: pickled dicts of numpy arrays need weights_only=False on torch >= 2.6; older torch has
+    no such argument"""
+    import torch
+
+    try:
+        return torch.load(path, weights_only=False)
+    except TypeError:  # torch < 1.13
+        return torch.load(path)
+
+
 def load_transitions(path):
     """reads a reference data file (any of generate_data / unite_data / extract_positives outputs) ->
     (rgb u8 [n,H,W,3], depth f32 [n,H,W], actions i64 [n], rewards i64 [n]).  The reference's generator can leave the lists
@@ -75,10 +86,7 @@ def load_transitions(path):
     the common prefix is returned."""
     import torch
 
-    try:
-        d = torch.load(path, weights_only=False)
-    except TypeError:  # torch < 1.13
-        d = torch.load(path)
+    d = _torch_load(path)
     states, actions, rewards = d["states"], d["actions"], d["rewards"]
     n = min(len(states), len(actions), len(rewards))
     if n == 0:
@@ -95,7 +103,7 @@ def unite(paths, out_path=None):
 
     final = defaultdict(list)
     for p in paths:
-        d = torch.load(p, weights_only=False)
+        d = _torch_load(p)
         for k in ("states", "actions", "rewards"):
             final[k] += d[k]
     if out_path:

@@ -11,7 +11,7 @@ environment pushes N transitions at once, and `sample` draws the SAME indices th
 positions through `randbelow` only, so sampling `range(len)` with the same generator state returns the indices of the
 elements the reference's list sampling returns.  By default the generator is Python's global `random` module seeded with
 20 exactly like the reference (the unchanged agent draws its epsilon from the same stream); pass `rng=random.Random(20)` for
-a private stream.  Storage and gathers are tensor plumbing (any torch device); there is no kernel here.
+a private stream (a generator passed in is used as it is, never re-seeded).  Storage and gathers are tensor plumbing (any torch device); there is no kernel here.
 """
 import random as _random
 
@@ -28,8 +28,10 @@ class DeviceReplayBuffer:
         self.rewards = torch.zeros(self.size, dtype=torch.float32, device=self.device)
         self.position = 0
         self.length = 0
+        # Modules.py:33 seeds the GLOBAL stream with 20; a caller-supplied generator keeps its own state, seed=None skips seeding
         self.rng = rng if rng is not None else _random
-        self.rng.seed(seed)  # Modules.py:33
+        if rng is None and seed is not None:
+            self.rng.seed(seed)
 
     def __len__(self):
         return self.length

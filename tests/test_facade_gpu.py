@@ -16,7 +16,7 @@ def env():
     sys.path.insert(0, COMPAT)
     import gym
 
-    e = gym.make("gym_grasper:Grasper-v0", show_obs=False, render=False, quiet=True)
+    e = gym.make("gym_grasper:Grasper-v0", file="/UR5+gripper/UR5gripper_2_finger.xml", show_obs=False, render=False, quiet=True)
     yield e
     e.close()
     sys.path.remove(COMPAT)
@@ -73,3 +73,41 @@ def test_controller_methods(env):
     c.stay(20)
     xyz = c.pixel_2_world(136, 80, 1.11)
     assert np.abs(xyz - [-0.16551974, -0.50804459, 0.88999999]).max() < 1e-6
+
+
+def test_open_loop_actuation_matches_oracle(env, scene_a):
+    """MJ_Controller.actuate_joint_group + sim.step() (MujocoController.py:256-267, :611): open-loop motor values, bare sub-steps"""
+    from oracle.oracle_py import OracleEnv
+
+    blob, A, _ = scene_a
+    np.random.seed(21)
+    env.reset()
+    q0, v0 = env.data.qpos.copy(), env.data.qvel.copy()
+    env.set_state(q0, v0)
+    c = env.controller
+    c.actuate_joint_group("Arm", [0.5, -0.25, 0.3, 0.1, -0.1])
+    c.actuate_joint_group("Gripper", [0.2])
+    assert np.allclose(np.asarray(env.data.ctrl), [0.5, -0.25, 0.3, 0.1, -0.1, 0.0, 0.2])
+    for _ in range(25):
+        env.sim.step()
+    o = OracleEnv(blob)
+    o.reset(q0, v0)
+    o.ctrl[:] = [0.5, -0.25, 0.3, 0.1, -0.1, 0.0, 0.2]
+    o.step(25)
+    assert np.abs(env.data.qpos - o.qpos).max() < 1e-9
+    assert np.abs(env.data.qvel - o.qvel).max() < 1e-7
+    o.close()
+    c.actuate_joint_group("Arm", [0.0] * 4)  # wrong length: printed and swallowed like the reference
+    c.move_group_to_joint_target(quiet=True, max_steps=50)  # the next closed-loop movement takes the controls back
+    env.sim.data.ctrl[:] = 0
+
+
+def test_default_scene_is_the_reference_default():
+    """GraspEnv() with no file = UR5gripper_2_finger_many_objects.xml (GraspingEnv.py:30); GRASP_SCENE=A is an announced override"""
+    from mujoco_rl_ur5_b200 import grasp_env
+
+    assert grasp_env._scene_key(None) == ("B", False) and grasp_env._scene_key(grasp_env.REFERENCE_DEFAULT_FILE) == ("B", False)
+    assert grasp_env._scene_key("/UR5+gripper/UR5gripper_2_finger.xml") == ("A", False)
+    e = grasp_env.GraspEnv(quiet=True, show_obs=False)
+    assert e.scene == "B" and e.engine.size(1) == 248
+    e.close()

@@ -44,8 +44,8 @@ def test_ring_and_sampling_golden():
 
 
 def test_push_batch_equals_consecutive_pushes():
-    a = DeviceReplayBuffer(8, state_shape=(1,), device="cpu", rng=random.Random())
-    b = DeviceReplayBuffer(8, state_shape=(1,), device="cpu", rng=random.Random())
+    a = DeviceReplayBuffer(8, state_shape=(1,), device="cpu", rng=random.Random(20))
+    b = DeviceReplayBuffer(8, state_shape=(1,), device="cpu", rng=random.Random(20))
     k = 0
     for n in (3, 4, 5, 11, 2):
         s = torch.arange(k, k + n, dtype=torch.float32)[:, None]
@@ -80,3 +80,15 @@ def test_same_samples_as_the_reference_class():
                      lambda B_: [int(t.state[0, 0, 0, 0]) for t in rb.sample(B_)], lambda: len(rb), n, size, B)
         ours = _ours(size, B, n)  # rng=None: the global `random` module, re-seeded with 20 by the constructor
         assert ours == ref
+
+
+def test_a_callers_generator_is_not_reseeded():
+    """the constructor used to call rng.seed(20) on a generator passed in, and on the global module whatever `seed`"""
+    r = random.Random(12345)
+    expect = random.Random(12345).random()
+    DeviceReplayBuffer(4, state_shape=(1,), device="cpu", rng=r)
+    assert r.random() == expect
+    random.seed(777)
+    expect = random.Random(777).random()
+    DeviceReplayBuffer(4, state_shape=(1,), device="cpu", seed=None)
+    assert random.random() == expect
