@@ -80,8 +80,10 @@ class BatchedGraspEnv:
         self.episode = 0
         self._pin_action = torch.empty((n_envs, 2), dtype=torch.int32).pin_memory()
         self._pin_reward = torch.empty(n_envs, dtype=torch.uint8).pin_memory()
+        self._pin_obs = None
         self.h2d_bytes_per_step = self._pin_action.numel() * 4
         self.d2h_bytes_per_step = self._pin_reward.numel()
+        self.obs_bytes = n_envs * image_width * image_height * (3 + 4)  # rgb u8 x3 + depth f32
 
     # ------------------------------------------------------------------ gym-like API
     def reset(self):
@@ -102,8 +104,10 @@ class BatchedGraspEnv:
         rgb, depth = self.engine.render(self.cam, self.IMAGE_WIDTH, self.IMAGE_HEIGHT)
         return {"rgb": rgb, "depth": depth}
 
-    def step(self, action):
-        """action: int array [N,2] (host).  Returns (obs, reward u8[N] host, done bool[N], info)."""
+    def step(self, action, obs_to_host=False):
+        """action: int array [N,2] (host).  Returns (obs, reward u8[N] host, done bool[N], info).  obs_to_host=True additionally
+        copies the new observation into pinned host buffers (`info["obs_host"]`), which is what the reference's single-env API hands
+        its caller every step; by default observations stay on the device for a device-side agent."""
         t = self.torch
         eng = self.engine
         if self.current_observation is None or self.step_called == 1:
@@ -128,9 +132,16 @@ class BatchedGraspEnv:
         reward = reward * execute.to(t.uint8)
         self._pin_reward.copy_(reward, non_blocking=True)
         self.current_observation = self.get_observation()
+        info = {"executed": execute}
+        if obs_to_host:
+            if self._pin_obs is None:
+                self._pin_obs = {k: t.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in self.current_observation.items()}
+            for k, v in self.current_observation.items():
+                self._pin_obs[k].copy_(v, non_blocking=True)
+            info["obs_host"] = self._pin_obs
         t.cuda.current_stream().synchronize()
         self.step_called += 1
-        return self.current_observation, self._pin_reward.numpy().copy(), np.zeros(self.n_envs, bool), {"executed": execute}
+        return self.current_observation, self._pin_reward.numpy().copy(), np.zeros(self.n_envs, bool), info
 
     def render(self, mode="rgb_array"):
         return self.get_observation()["rgb"]

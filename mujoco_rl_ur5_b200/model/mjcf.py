@@ -102,11 +102,14 @@ def _expand_includes(node, base_dir):
             _expand_includes(ch, base_dir)
 
 
-def compile_mjcf(path):
-    """Parse `path` and return a dict of numpy arrays (the model)."""
+def compile_mjcf(path, transform=None):
+    """Parse `path` and return a dict of numpy arrays (the model).  `transform(root)`: optional edit of the parsed element tree
+    (after include expansion) before compilation - used for scene variants that the reference realised by editing the XML."""
     base_dir = os.path.dirname(os.path.abspath(path))
     root = ET.parse(path).getroot()
     _expand_includes(root, base_dir)
+    if transform is not None:
+        transform(root)
     comp = root.find("compiler").attrib if root.find("compiler") is not None else {}
     assert comp.get("angle", "degree") == "radian", "only angle=radian scenes are supported"
     inertiafromgeom = comp.get("inertiafromgeom", "auto") == "true"

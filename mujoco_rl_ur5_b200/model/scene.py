@@ -16,7 +16,23 @@ REFERENCE_DIR = os.environ.get("GRASP_REFERENCE_DIR", "/root/reference")
 SCENES = {
     "A": "UR5+gripper/UR5gripper_2_finger.xml",            # 6 objects, condim 4 (BASELINE configs 1-4)
     "B": "UR5+gripper/UR5gripper_2_finger_many_objects.xml",  # 40 free objects, condim 6 (GraspingEnv.py:30 default)
+    # BASELINE config 3 "fixed-size objects" = the reference's iteration 1, "objects of equal size" (README.md:20): the 6-object
+    # scene with every graspable object turned into the 4 cm cube of box_1 (UR5gripper_2_finger.xml:238)
+    "A1": "UR5+gripper/UR5gripper_2_finger.xml",
 }
+OBJECT_GEOMS_A = ("box_1", "box_2", "box_3", "ball_1", "ball_2", "ball_3")
+
+
+def _equal_size_objects(root):
+    n = 0
+    for g in root.iter("geom"):
+        if g.attrib.get("name") in OBJECT_GEOMS_A:
+            g.attrib["type"], g.attrib["size"] = "box", "0.02 0.02 0.02"
+            n += 1
+    assert n == len(OBJECT_GEOMS_A), n
+
+
+TRANSFORMS = {"A1": _equal_size_objects}
 
 # PID gains after p_scale=3, d_scale=0.1 (MujocoController.py:157-235); Ki = 0 everywhere
 PID_KP = np.array([7, 10, 5, 7, 5, 5, 2.5]) * 3.0
@@ -35,7 +51,7 @@ MATERIAL_RGB = {"ur5_mat": (0.45, 0.45, 0.45), "gripper_mat": (0.45, 0.45, 0.45)
 
 def compile_scene(key, reference_dir=None):
     path = os.path.join(reference_dir or REFERENCE_DIR, SCENES[key])
-    M = compile_mjcf(path)
+    M = compile_mjcf(path, TRANSFORMS.get(key))
     names = M["_names"]
     M["pid_kp"], M["pid_kd"], M["pid_lim"] = PID_KP, PID_KD, PID_LIM
     M["ik_chain"], M["ik_lower"], M["ik_upper"], M["ik_offset"] = IK_CHAIN, IK_LOWER, IK_UPPER, IK_OFFSET
@@ -82,7 +98,7 @@ def load_scene(key="A"):
     return arrays, names
 
 
-def build_assets(keys=("A", "B")):
+def build_assets(keys=("A", "B", "A1")):
     import json
 
     os.makedirs(ASSET_DIR, exist_ok=True)
