@@ -219,34 +219,52 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
 }
 
 // Dense Cholesky + forward/backward substitution of one tree block (rows lo .. lo+nt-1 of the packed matrix, nt <= GE_GROUP)
-// inside an 8-lane group: lane l owns row lo + l.  x[row] := sign * (H_block^-1 g)[row].
-__device__ __forceinline__ void group_chol_solve(double* H, int lo, int nt, int l, unsigned gmask, const double* g_, double* x, double sign) {
+// inside an 8-lane group, entirely in REGISTERS: lane l loads row lo + l of the block once (static register indices, the loops are
+// fully unrolled), the factorisation exchanges pivots / column entries through shuffles, nothing is written back to the matrix
+// (the factor is used exactly once).  Rows l >= nt are padded with the identity.  x[row] := sign * (H_block^-1 g)[row].
+// (r02: the shared-memory version spent ~1000 instructions per block in packed-index arithmetic, LDS/STS and three __syncwarp per
+// column; mass_block_solve + the group path of cholesky_solve were 22 % of k_run's time.)
+__device__ __forceinline__ void group_chol_solve(const double* H, int lo, int nt, int l, unsigned gmask, const double* g_, double* x, double sign) {
   const int row = lo + l;
   const bool mine = l < nt;
-  for (int j = 0; j < nt; j++) {
-    double d = H[HIDX(lo + j, lo + j)];
+  double r[GE_GROUP], inv[GE_GROUP];
+#pragma unroll
+  for (int j = 0; j < GE_GROUP; j++) r[j] = (mine && j <= l) ? H[HIDX(row, lo + j)] : (j == l ? 1.0 : 0.0);
+  // right-looking Cholesky: after step j, r[j] holds L[l][j] (rows l >= j), later columns carry the Schur complement
+#pragma unroll
+  for (int j = 0; j < GE_GROUP; j++) {
+    double d = __shfl_sync(gmask, r[j], j, GE_GROUP);
     if (d < GE_MINVAL) d = GE_MINVAL;
-    double ljj = sqrt(d), inv = 1.0 / ljj;
-    __syncwarp(gmask);
-    if (mine && l > j) H[HIDX(row, lo + j)] *= inv;
-    if (l == j) H[HIDX(row, row)] = ljj;
-    __syncwarp(gmask);
-    if (mine && l > j) {
-      double lij = H[HIDX(row, lo + j)];
-      for (int k = j + 1; k <= l; k++) H[HIDX(row, lo + k)] -= lij * H[HIDX(lo + k, lo + j)];
+    const double ljj = sqrt(d);
+    inv[j] = 1.0 / ljj;
+    if (l > j) r[j] *= inv[j];
+    else if (l == j) r[j] = ljj;
+#pragma unroll
+    for (int k = j + 1; k < GE_GROUP; k++) {
+      const double lkj = __shfl_sync(gmask, r[j], k, GE_GROUP);  // L[k][j]
+      if (l >= k) r[k] -= r[j] * lkj;
     }
-    __syncwarp(gmask);
   }
   double y = mine ? g_[row] : 0.0;  // L y = g (column oriented): after column j every later row subtracts L[row][j] y_j
-  for (int j = 0; j < nt; j++) {
-    double yj = __shfl_sync(gmask, y, j, GE_GROUP) / H[HIDX(lo + j, lo + j)];
+#pragma unroll
+  for (int j = 0; j < GE_GROUP; j++) {
+    const double yj = __shfl_sync(gmask, y, j, GE_GROUP) * inv[j];
     if (l == j) y = yj;
-    else if (mine && l > j) y -= H[HIDX(row, lo + j)] * yj;
+    else if (l > j) y -= r[j] * yj;
   }
-  for (int i = nt - 1; i >= 0; i--) {  // L^T x = y
-    double xi = __shfl_sync(gmask, y, i, GE_GROUP) / H[HIDX(lo + i, lo + i)];
+#pragma unroll
+  for (int i = GE_GROUP - 1; i >= 0; i--) {  // L^T x = y: row l needs L[i][l] (i > l), which lives in lane i's register r[l]
+    const double xi = __shfl_sync(gmask, y, i, GE_GROUP) * inv[i];
+    double lil = 0.0;
+#pragma unroll
+    for (int c = 0; c < GE_GROUP; c++) {
+      if (c < i) {  // compile-time after unrolling
+        const double v = __shfl_sync(gmask, r[c], i, GE_GROUP);
+        if (l == c) lil = v;
+      }
+    }
     if (l == i) y = xi;
-    else if (mine && l < i) y -= H[HIDX(lo + i, row)] * xi;
+    else if (l < i) y -= lil * xi;
   }
   if (mine) x[row] = sign * y;
 }

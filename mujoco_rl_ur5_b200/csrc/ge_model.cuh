@@ -74,5 +74,7 @@ struct EnvArrays {
   int* status;                    // [N]
   long long* substeps;            // [N]
   int* busy_count;                // [1]
+  int* lock;                      // [N] 1 while a warp of k_run holds the env (dynamic env -> warp assignment)
+  unsigned long long* ticket;     // [1] monotonically increasing task counter of k_run (never reset: launches subtract their base)
   double* gws;                    // [N, total_bytes/8] workspace rows when Layout::ws_global
 };

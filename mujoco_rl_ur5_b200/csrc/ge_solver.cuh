@@ -248,7 +248,7 @@ namespace ge {
 // CTA barriers inside the FIRST Newton iteration (which every stepping warp executes): keeps the warps of a CTA on the same
 // code so that they share instruction-cache lines; later iterations run unsynchronised.
 #define GE_NEWTON_BARRIERS 4
-__device__ __forceinline__ void newton_barrier(bool sync) { if (sync) __syncthreads(); }
+__device__ __forceinline__ void newton_barrier(bool sync) { if (sync) asm volatile("barrier.sync 1, %0;" ::"r"((int)(blockDim.x * blockDim.y)) : "memory"); }
 
 __device__ __noinline__ int solve_newton(double* ws, int* wi, int lane, int ncon, int nsr, bool sync = false) {
   const DevModel& m = c_m; const Layout& L = c_L;

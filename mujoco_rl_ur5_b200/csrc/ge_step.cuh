@@ -21,8 +21,16 @@ struct StepInfo { int ncon, nsr, niter; };
 #define GE_STAGE_SYNC 1
 #endif
 #define GE_NUM_STAGE_BARRIERS (3 + GE_NEWTON_BARRIERS)
-__device__ __forceinline__ void stage_barrier(bool sync) { if (GE_STAGE_SYNC && sync) __syncthreads(); }
-__device__ __forceinline__ void stage_barriers_idle(bool on) { if (GE_STAGE_SYNC && on) for (int k = 0; k < GE_NUM_STAGE_BARRIERS; k++) __syncthreads(); }
+// The warps of a CTA reach these barriers from DIFFERENT code locations (a stepping warp inside forward() / solve_newton(), a warp
+// whose environment does not step this iteration in stage_barriers_idle()).  That is legal for the unaligned PTX barrier
+// (`barrier.sync id, count`: any convergent warp may arrive from anywhere, the hardware counts arrivals) but not for __syncthreads()
+// (`barrier.sync.aligned` semantics in CUDA C++; compute-sanitizer synccheck reported "divergent thread(s) in block", r02b), so the
+// stage barriers use named barrier 1 with the CTA's thread count.
+__device__ __forceinline__ void cta_barrier_unaligned() {
+  asm volatile("barrier.sync 1, %0;" ::"r"((int)(blockDim.x * blockDim.y)) : "memory");
+}
+__device__ __forceinline__ void stage_barrier(bool sync) { if (GE_STAGE_SYNC && sync) cta_barrier_unaligned(); }
+__device__ __forceinline__ void stage_barriers_idle(bool on) { if (GE_STAGE_SYNC && on) for (int k = 0; k < GE_NUM_STAGE_BARRIERS; k++) cta_barrier_unaligned(); }
 
 // mj_forward: kinematics -> bias -> mass matrix -> collision -> constraints -> smooth acceleration -> Newton
 __device__ __noinline__ StepInfo forward(double* ws, int* wi, int lane, int* status, bool sync = false) {

@@ -26,83 +26,129 @@ extern "C" const char* ge_last_error(void) { return g_err; }
 extern "C" const char* ge_version(void) { return GE_WS_IN_HBM ? "grasp_engine 0.2 sm_100a fp64 warp-per-env (workspace: HBM rows)" : "grasp_engine 0.2 sm_100a fp64 warp-per-env (workspace: shared memory)"; }
 
 // ------------------------------------------------------------------------------------------------ kernels
-// Sub-step kernel: one warp per environment.  Loads the env's state rows into its shared-memory slice, runs up to `nsub`
-// iterations of the reference control loop (PID -> mj_step) including movement / grasp-program transitions, writes back.
-// A CTA holds `blockDim.y` warps (= environments); they meet at one barrier per sub-step so that the warps of an SM walk the
-// (large) sub-step code roughly together and share instruction-cache lines.
+// Sub-step kernel: one warp per environment, environments handed to warps DYNAMICALLY.
+// A launch gives every environment a budget of `nsub` iterations of the reference control loop (PID -> mj_step, including the
+// movement / grasp-program transitions), split into visits of `quota` iterations.  Task t of a launch = (visit t / n_env, env t % n_env);
+// a warp that has no environment takes the next task from a global counter, skips it if the environment is idle or another warp
+// still holds it (per-env lock, never waited for), otherwise loads the env's state rows into its shared-memory slice, runs the
+// visit and writes the rows back.  The grid is persistent (<= the resident CTAs), so 4096 envs on 1184 warp slots cost 13.84 -> 14
+// rounds of 64 iterations instead of 3.46 -> 4 rounds of 256, finished or idle environments stop costing anything, and the tail
+// of a batch of unequal grasp attempts is spread over all SMs.  Arithmetic per env is unchanged: the state crosses HBM in full
+// fp64 between visits, so a trajectory does not depend on how its iterations were cut.
+// A CTA holds `blockDim.y` warps; they meet at one barrier per iteration (+ the stage barriers) so that the warps of an SM walk
+// the (large) sub-step code roughly together and share instruction-cache lines.
 namespace ge {
-__global__ void __launch_bounds__(256) k_run(EnvArrays E, int n_env, int nsub, double base_x, double base_y, double base_z, int stage_sync) {
-  extern __shared__ double smem[];
+struct EnvRegs {
+  Cmd c; Prog p; int info[12]; unsigned char reward; int status; long long nstep;
+};
+__device__ __forceinline__ bool env_is_busy(const EnvArrays& E, int env) { return __ldcg(E.cmd_active + env) != 0 || __ldcg(E.prog_phase + env) != PH_NONE; }
+__device__ __forceinline__ void env_load(const EnvArrays& E, int env, double* ws, int lane, EnvRegs& r) {
   const DevModel& m = c_m; const Layout& L = c_L;
-  int env = blockIdx.x * blockDim.y + threadIdx.y, lane = threadIdx.x;
-  bool valid = env < n_env;
-  Cmd c;
-  c.active = valid ? E.cmd_active[env] : 0;
-  Prog p;
-  p.phase = valid ? E.prog_phase[env] : PH_NONE;
-  bool busy = c.active || p.phase != PH_NONE;
-  if (!__syncthreads_or(busy)) return;
-#if GE_WS_IN_HBM
-  double* ws = E.gws + (size_t)(valid ? env : 0) * (L.total_bytes / 8);
-#else
-  double* ws = smem + (size_t)threadIdx.y * (L.total_bytes / 8);
-#endif
-  int* wi = (int*)(ws + L.total_doubles);
-  int info[12];
-  unsigned char reward = 0;
-  int status = 0;
-  long long nstep = 0;
-  c.reached = 0;
-  if (busy) {
-    c.mask = E.cmd_mask[env]; c.maxsteps = E.cmd_maxsteps[env]; c.steps = E.cmd_steps[env]; c.result = E.cmd_result[env]; c.tol = E.cmd_tol[env];
-    p.rot = E.prog_rot[env]; p.grasp = E.prog_grasp[env]; p.aux = E.prog_aux[env] & 0xffff; p.r1 = (E.prog_aux[env] >> 16) & 0xf; p.rfinal = ((E.prog_aux[env] >> 20) & 0xf) - 1;
-    for (int k = 0; k < 3; k++) p.coords[k] = E.prog_coords[3 * env + k];
-    p.table = E.prog_table[env];
-    for (int k = 0; k < 12; k++) info[k] = E.prog_info[12 * env + k];
-    reward = E.reward[env];
-    status = E.status[env];
-    LANE_LOOP(i, m.nq) ws[L.qpos + i] = E.qpos[(size_t)env * m.nq + i];
-    LANE_LOOP(i, m.nv) { ws[L.qvel + i] = E.qvel[(size_t)env * m.nv + i]; ws[L.qaccws + i] = E.qaccws[(size_t)env * m.nv + i]; }
-    ws[L.ctl + lane] = E.ctl[(size_t)env * 32 + lane];
-    __syncwarp();
-  }
-  const double base[3] = {base_x, base_y, base_z};
-  bool running = busy;
-  for (int it = 0; it < nsub; it++) {
-    if (!__syncthreads_or(running)) break;
-    if (!running) { stage_barriers_idle(stage_sync != 0); continue; }
-    bool stepped = false;
-    // one iteration of the reference loop that ends in a physics step (or the env going idle)
-    while (true) {
-      if (!c.active) {
-        if (p.phase == PH_NONE || !prog_advance(p, c, ws, lane, base, info, &reward)) { running = false; break; }
-        continue;
-      }
-      double delta = pid_and_delta(ws, lane, c.mask, m.timestep);
-      if (delta < c.tol) { c.result = 1; c.reached = 1; }
-      if (c.steps > c.maxsteps) { c.result = 2; c.active = 0; continue; }
-      sim_step(ws, wi, lane, &status, stage_sync != 0);
-      stepped = true;
-      c.steps++; nstep++;
-      if (c.reached) c.active = 0;
-      break;
-    }
-    if (!stepped) stage_barriers_idle(stage_sync != 0);
-  }
-  if (!busy) return;
-  // a movement that just ended inside the last iteration still has to hand over to the program (no sub-step involved)
-  while (!c.active && p.phase != PH_NONE) { if (!prog_advance(p, c, ws, lane, base, info, &reward)) break; }
+  r.c.active = __ldcg(E.cmd_active + env); r.p.phase = __ldcg(E.prog_phase + env);
+  r.c.mask = __ldcg(E.cmd_mask + env); r.c.maxsteps = __ldcg(E.cmd_maxsteps + env); r.c.steps = __ldcg(E.cmd_steps + env);
+  r.c.result = __ldcg(E.cmd_result + env); r.c.tol = __ldcg(E.cmd_tol + env); r.c.reached = 0;
+  int aux = __ldcg(E.prog_aux + env);
+  r.p.rot = __ldcg(E.prog_rot + env); r.p.grasp = __ldcg(E.prog_grasp + env); r.p.aux = aux & 0xffff; r.p.r1 = (aux >> 16) & 0xf; r.p.rfinal = ((aux >> 20) & 0xf) - 1;
+  for (int k = 0; k < 3; k++) r.p.coords[k] = __ldcg(E.prog_coords + 3 * env + k);
+  r.p.table = __ldcg(E.prog_table + env);
+  for (int k = 0; k < 12; k++) r.info[k] = __ldcg(E.prog_info + 12 * env + k);
+  r.reward = __ldcg(E.reward + env); r.status = __ldcg(E.status + env); r.nstep = 0;
+  LANE_LOOP(i, m.nq) ws[L.qpos + i] = __ldcg(E.qpos + (size_t)env * m.nq + i);
+  LANE_LOOP(i, m.nv) { ws[L.qvel + i] = __ldcg(E.qvel + (size_t)env * m.nv + i); ws[L.qaccws + i] = __ldcg(E.qaccws + (size_t)env * m.nv + i); }
+  ws[L.ctl + lane] = __ldcg(E.ctl + (size_t)env * 32 + lane);
+  __syncwarp();
+}
+__device__ __forceinline__ void env_store(const EnvArrays& E, int env, const double* ws, int lane, const EnvRegs& r) {
+  const DevModel& m = c_m; const Layout& L = c_L;
   LANE_LOOP(i, m.nq) E.qpos[(size_t)env * m.nq + i] = ws[L.qpos + i];
   LANE_LOOP(i, m.nv) { E.qvel[(size_t)env * m.nv + i] = ws[L.qvel + i]; E.qaccws[(size_t)env * m.nv + i] = ws[L.qaccws + i]; }
   E.ctl[(size_t)env * 32 + lane] = ws[L.ctl + lane];
   if (lane == 0) {
-    E.cmd_active[env] = c.active; E.cmd_mask[env] = c.mask; E.cmd_maxsteps[env] = c.maxsteps; E.cmd_steps[env] = c.steps;
-    E.cmd_result[env] = c.result; E.cmd_tol[env] = c.tol;
-    E.prog_phase[env] = p.phase; E.prog_grasp[env] = p.grasp; E.prog_aux[env] = (p.aux & 0xffff) | ((p.r1 & 0xf) << 16) | (((p.rfinal + 1) & 0xf) << 20);
-    for (int k = 0; k < 12; k++) E.prog_info[12 * env + k] = info[k];
-    E.reward[env] = reward; E.status[env] = status; E.substeps[env] += nstep;
-    if (c.active || p.phase != PH_NONE) atomicAdd(E.busy_count, 1);
+    E.cmd_active[env] = r.c.active; E.cmd_mask[env] = r.c.mask; E.cmd_maxsteps[env] = r.c.maxsteps; E.cmd_steps[env] = r.c.steps;
+    E.cmd_result[env] = r.c.result; E.cmd_tol[env] = r.c.tol;
+    E.prog_phase[env] = r.p.phase; E.prog_grasp[env] = r.p.grasp;
+    E.prog_aux[env] = (r.p.aux & 0xffff) | ((r.p.r1 & 0xf) << 16) | (((r.p.rfinal + 1) & 0xf) << 20);
+    for (int k = 0; k < 12; k++) E.prog_info[12 * env + k] = r.info[k];
+    E.reward[env] = r.reward; E.status[env] = r.status; E.substeps[env] += r.nstep;
   }
+}
+
+__global__ void __launch_bounds__(256) k_run(EnvArrays E, int n_env, int nsub, int quota, unsigned long long ticket_base, double base_x, double base_y,
+                                             double base_z, int stage_sync) {
+  extern __shared__ double smem[];
+  const Layout& L = c_L;
+  const int lane = threadIdx.x;
+  const int visits = (nsub + quota - 1) / quota;
+  const unsigned long long total = (unsigned long long)n_env * visits;
+  const double base[3] = {base_x, base_y, base_z};
+#if !GE_WS_IN_HBM
+  double* ws = smem + (size_t)threadIdx.y * (L.total_bytes / 8);
+#else
+  double* ws = nullptr;
+#endif
+  int* wi = nullptr;
+  EnvRegs r;
+  int env = -1, left = 0;
+  bool exhausted = false, running = false;
+  for (;;) {
+    // ---- a warp without an environment takes tasks until it finds a busy, unlocked environment (or the launch has none left)
+    while (env < 0 && !exhausted) {
+      unsigned long long t = 0;
+      if (lane == 0) t = atomicAdd(E.ticket, 1ULL) - ticket_base;
+      t = __shfl_sync(FULL, t, 0);
+      if (t >= total) { exhausted = true; break; }
+      const int e = (int)(t % (unsigned long long)n_env), v = (int)(t / (unsigned long long)n_env);
+      if (!env_is_busy(E, e)) continue;
+      int got = 0;
+      if (lane == 0) got = atomicCAS(E.lock + e, 0, 1) == 0;
+      got = __shfl_sync(FULL, got, 0);
+      if (!got) continue;  // an earlier visit of this env is still running on another warp: this visit is dropped, never waited for
+      __threadfence();
+      if (!env_is_busy(E, e)) { __syncwarp(); if (lane == 0) atomicExch(E.lock + e, 0); continue; }
+#if GE_WS_IN_HBM
+      ws = E.gws + (size_t)e * (L.total_bytes / 8);
+#endif
+      wi = (int*)(ws + L.total_doubles);
+      env_load(E, e, ws, lane, r);
+      env = e; running = true;
+      left = nsub - v * quota < quota ? nsub - v * quota : quota;
+    }
+    if (!__syncthreads_or(env >= 0)) break;
+    if (env < 0) { stage_barriers_idle(stage_sync != 0); continue; }
+    bool stepped = false;
+    // one iteration of the reference loop that ends in a physics step (or the env going idle)
+    while (true) {
+      if (!r.c.active) {
+        if (r.p.phase == PH_NONE || !prog_advance(r.p, r.c, ws, lane, base, r.info, &r.reward)) { running = false; break; }
+        continue;
+      }
+      double delta = pid_and_delta(ws, lane, r.c.mask, c_m.timestep);
+      if (delta < r.c.tol) { r.c.result = 1; r.c.reached = 1; }
+      if (r.c.steps > r.c.maxsteps) { r.c.result = 2; r.c.active = 0; continue; }
+      sim_step(ws, wi, lane, &r.status, stage_sync != 0);
+      stepped = true;
+      r.c.steps++; r.nstep++;
+      if (r.c.reached) r.c.active = 0;
+      break;
+    }
+    if (!stepped) stage_barriers_idle(stage_sync != 0);
+    if (--left <= 0 || !running) {
+      // a movement that just ended inside the last iteration still has to hand over to the program (no sub-step involved)
+      while (!r.c.active && r.p.phase != PH_NONE) { if (!prog_advance(r.p, r.c, ws, lane, base, r.info, &r.reward)) break; }
+      env_store(E, env, ws, lane, r);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicExch(E.lock + env, 0);
+      env = -1;
+    }
+  }
+}
+// number of environments that still have a movement / program pending (ge_run's loop condition)
+__global__ void k_count_busy(EnvArrays E, int n_env) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  int b = env < n_env && (E.cmd_active[env] || E.prog_phase[env] != PH_NONE);
+  unsigned m = __ballot_sync(FULL, b);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(E.busy_count, __popc(m));
 }
 
 // forward pipeline on one env, selected intermediate copied out (parity tests); no integration
@@ -295,6 +341,9 @@ struct ge_engine {
   int64_t launches, substep_launches;
   int wpb;           // warps (= envs) per CTA of the sub-step kernel
   int stage_sync;    // CTA barriers between the stages of a sub-step (instruction-cache sharing)
+  int quota;         // iterations per visit of k_run's dynamic env scheduling
+  int max_ctas;      // resident CTAs of k_run on this device (persistent grid)
+  unsigned long long ticket_base;  // tasks issued by all previous launches
   int* d_nout; double* d_dbg;
   RenderCtx rctx;
 };
@@ -486,7 +535,16 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
   AL(E.cmd_mask, int, N); AL(E.cmd_maxsteps, int, N); AL(E.cmd_steps, int, N); AL(E.cmd_result, int, N); AL(E.cmd_active, int, N); AL(E.cmd_tol, double, N);
   AL(E.prog_phase, int, N); AL(E.prog_rot, int, N); AL(E.prog_grasp, int, N); AL(E.prog_aux, int, N); AL(E.prog_info, int, N * 12);
   AL(E.prog_coords, double, N * 3); AL(E.prog_table, double, N); AL(E.reward, unsigned char, N); AL(E.status, int, N); AL(E.substeps, long long, N);
-  AL(E.busy_count, int, 1);
+  AL(E.busy_count, int, 1); AL(E.lock, int, N); AL(E.ticket, unsigned long long, 1);
+  h->ticket_base = 0;
+  h->quota = 64;
+  if (const char* ev = getenv("GE_QUOTA")) { int v = atoi(ev); if (v >= 1) h->quota = v; }
+  {
+    int per_sm = 0, sms = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_run, 32 * h->wpb, (size_t)h->wpb * h->ws_smem));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    h->max_ctas = per_sm * sms > 0 ? per_sm * sms : 1;
+  }
   E.gws = nullptr;
   if (h->lay.ws_global) { AL(E.gws, double, N * (size_t)(h->lay.total_bytes / 8)); }
   AL(h->d_nout, int, 1); AL(h->d_dbg, double, 1 << 16);
@@ -519,7 +577,7 @@ extern "C" int ge_destroy(ge_handle h) {
   EnvArrays& E = h->E;
   void* ptrs[] = {E.qpos, E.qvel, E.qaccws, E.ctl, E.cmd_mask, E.cmd_maxsteps, E.cmd_steps, E.cmd_result, E.cmd_active, E.cmd_tol, E.prog_phase,
                   E.prog_rot, E.prog_grasp, E.prog_aux, E.prog_info, E.prog_coords, E.prog_table, E.reward, E.status, E.substeps, E.busy_count,
-                  h->d_nout, h->d_dbg, h->dblob, E.gws};
+                  h->d_nout, h->d_dbg, h->dblob, E.gws, E.lock, E.ticket};
   for (void* p : ptrs) cudaFree(p);
   render_free(h->rctx);
   delete h;
@@ -610,8 +668,13 @@ extern "C" int ge_run_async(ge_handle h, int substeps) {
   if (!h || substeps <= 0) return fail(GE_ERR_ARG, "ge_run_async: bad argument");
   if (bind(h)) return GE_ERR_CUDA;
   dim3 blk(32, h->wpb);
-  k_run<<<(h->n_envs + h->wpb - 1) / h->wpb, blk, (size_t)h->wpb * h->ws_smem, h->stream>>>(h->E, h->n_envs, substeps, h->base_pos[0], h->base_pos[1],
-                                                                                                   h->base_pos[2], h->stage_sync);
+  int ctas = (h->n_envs + h->wpb - 1) / h->wpb;
+  if (ctas > h->max_ctas) ctas = h->max_ctas;  // persistent grid: environments are handed to warps dynamically
+  int quota = h->quota < substeps ? h->quota : substeps;
+  k_run<<<ctas, blk, (size_t)h->wpb * h->ws_smem, h->stream>>>(h->E, h->n_envs, substeps, quota, h->ticket_base, h->base_pos[0], h->base_pos[1],
+                                                                h->base_pos[2], h->stage_sync);
+  // every warp takes tasks until it has drawn one beyond the launch's range: n_env * visits real tasks + one overshoot per warp
+  h->ticket_base += (unsigned long long)h->n_envs * ((substeps + quota - 1) / quota) + (unsigned long long)ctas * h->wpb;
   h->launches++; h->substep_launches++;
   CK(cudaGetLastError());
   return GE_OK;
@@ -627,6 +690,8 @@ extern "C" int ge_run(ge_handle h, int max_substeps, int* n_busy) {
     CK(cudaMemsetAsync(h->E.busy_count, 0, sizeof(int), h->stream));
     int r = ge_run_async(h, n);
     if (r) return r;
+    k_count_busy<<<(h->n_envs + 127) / 128, 128, 0, h->stream>>>(h->E, h->n_envs);
+    h->launches++;
     CK(cudaMemcpyAsync(&busy, h->E.busy_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     done += n;
