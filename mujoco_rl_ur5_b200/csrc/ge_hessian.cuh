@@ -40,14 +40,19 @@ __device__ __forceinline__ void jac_column(const double* c, int dim, const doubl
   }
 }
 
+// owner warp of the island a coupled tree belongs to (CTA-per-env build: islands are dealt out to the warps; their Hessian blocks
+// are disjoint, so the warps never touch the same entry)
+__device__ __forceinline__ int island_owner(const int* island, int t) { return island[t] % GE_NW; }
+
 __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int nsr, int lane) {
   const DevModel& m = c_m; const Layout& L = c_L;
   double* H = ws + L.H;
   const double *qM = ws + L.qM, *cdof = ws + L.cdof;
+  const int wl = lane & 31, wid = lane >> 5;
   int* tcoupled = wi + L.i_tcoupled;
   // ---- which trees are coupled to another tree by an active constraint (trees wider than a lane group take the coupled path too)
   LANE_LOOP(t, m.ntree) tcoupled[t] = m.tree_dofnum[t] > GE_GROUP ? 1 : 0;
-  __syncwarp();
+  gsync();
   LANE_LOOP(ci, ncon) {
     if (!wi[L.i_cact + ci]) continue;
     int t1 = wi[L.i_ct1 + ci], t2 = wi[L.i_ct2 + ci];
@@ -58,7 +63,7 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
     int A = wi[L.i_srA + i], B = wi[L.i_srB + i];
     if (B >= 0 && m.dof_treeindex[A] != m.dof_treeindex[B]) { tcoupled[m.dof_treeindex[A]] = 1; tcoupled[m.dof_treeindex[B]] = 1; }
   }
-  __syncwarp();
+  gsync();
   // ---- rows of M (zero-filled down to the tree root = dense block envelope)
   LANE_LOOP(i, m.nv) {
     int root = m.tree_dofadr[m.dof_treeindex[i]];
@@ -66,7 +71,7 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
     int a = m.dof_Madr[i], k = 0;
     for (int j = i; j >= 0; j = m.dof_parentid[j], k++) H[HIDX(i, j)] = qM[a + k];
   }
-  __syncwarp();
+  gsync();
   // ---- per-tree lists of the active contacts that live entirely inside one uncoupled tree (one lane per tree scans the contacts)
   int *tcount = wi + L.i_tcount, *tlist = wi + L.i_tlist;
   LANE_LOOP(t, m.ntree) {
@@ -78,13 +83,13 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
     }
     tcount[t] = cnt;
   }
-  __syncwarp();
-  // ---- uncoupled trees: one 8-lane group per tree, 4 trees at a time, every group walking ITS OWN contact list so that the four
-  // groups really run concurrently (same instruction stream, different contacts).  Lane l of a group owns dof lo + l; the
+  gsync();
+  // ---- uncoupled trees: one 8-lane group per tree, GE_LANES / 8 trees at a time, every group walking ITS OWN contact list so that
+  // the groups really run concurrently (same instruction stream, different contacts).  Lane l of a group owns dof lo + l; the
   // contact's Jacobian block is rebuilt in registers and J^T W J is added to the tree's dense block through shuffles.
   {
-    const int g = lane / GE_GROUP, l = lane % GE_GROUP;
-    for (int t0 = 0; t0 < m.ntree; t0 += 32 / GE_GROUP) {
+    const int g = lane / GE_GROUP, l = lane % GE_GROUP, gw = wl & ~(GE_GROUP - 1);  // gw: first lane of my group inside my warp
+    for (int t0 = 0; t0 < m.ntree; t0 += GE_LANES / GE_GROUP) {
       const int t = t0 + g;
       const bool valid = t < m.ntree && !tcoupled[t];
       const int lo = valid ? m.tree_dofadr[t] : 0, nt = valid ? m.tree_dofnum[t] : 0, cnt = valid ? tcount[t] : 0;
@@ -107,10 +112,11 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
         }
         for (int f = 0; f < GE_GROUP; f++) {
           double h = 0;
-          for (int k = 0; k < m.maxdim; k++) h += tw[k] * __shfl_sync(FULL, J[k], g * GE_GROUP + f);
+          for (int k = 0; k < m.maxdim; k++) h += tw[k] * __shfl_sync(FULL, J[k], gw + f);
           if (act && l >= f && f < nt && h != 0.0) H[HIDX(lo + l, lo + f)] += h;
         }
       }
+      __syncwarp();
       if (valid && l == 0)
         for (int i = 0; i < nsr; i++) {
           if (!wi[L.i_sract + i]) continue;
@@ -127,7 +133,7 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
       __syncwarp();
     }
   }
-  __syncwarp();
+  gsync();
   bool any_coupled = false;
   for (int t = 0; t < m.ntree; t++) any_coupled |= tcoupled[t] != 0;
   if (!any_coupled) return;
@@ -137,15 +143,15 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
   // (the fixed point - the smallest tree index of the component - does not depend on the order of the updates).
   int* island = wi + L.i_island;
   LANE_LOOP(t, m.ntree) island[t] = t;
-  __syncwarp();
+  gsync();
   for (int iter = 0; iter < m.ntree; iter++) {
-    int changed = 0;
+    bool changed = false;
     LANE_LOOP(ci, ncon) {
       if (!wi[L.i_cact + ci]) continue;
       int t1 = wi[L.i_ct1 + ci], t2 = wi[L.i_ct2 + ci];
       if (t1 < 0 || t2 < 0 || t1 == t2) continue;
       int a = ((volatile int*)island)[t1], b = ((volatile int*)island)[t2];
-      if (a != b) { int mn = a < b ? a : b; atomicMin(island + t1, mn); atomicMin(island + t2, mn); changed = 1; }
+      if (a != b) { int mn = a < b ? a : b; atomicMin(island + t1, mn); atomicMin(island + t2, mn); changed = true; }
     }
     LANE_LOOP(i, nsr) {
       if (!wi[L.i_sract + i]) continue;
@@ -154,10 +160,10 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
       int t1 = m.dof_treeindex[A], t2 = m.dof_treeindex[B];
       if (t1 == t2) continue;
       int a = ((volatile int*)island)[t1], b = ((volatile int*)island)[t2];
-      if (a != b) { int mn = a < b ? a : b; atomicMin(island + t1, mn); atomicMin(island + t2, mn); changed = 1; }
+      if (a != b) { int mn = a < b ? a : b; atomicMin(island + t1, mn); atomicMin(island + t2, mn); changed = true; }
     }
-    changed = __any_sync(FULL, changed);
-    __syncwarp();
+    changed = group_any(changed);
+    gsync();
     if (!changed) break;
   }
   // zero fill of the part of each coupled row that lies in the other (lower-numbered) trees of its island
@@ -171,13 +177,15 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
       for (int j = lo; j < hi; j++) H[HIDX(i, j)] = 0;
     }
   }
-  __syncwarp();
-  // ---- pass 2: warp-cooperative accumulation, one lane per dof of the contact
+  gsync();
+  // ---- pass 2: warp-cooperative accumulation, one lane per dof of the contact; a contact belongs to the warp that owns its island
   for (int ci = 0; ci < ncon; ci++) {
     int mask = wi[L.i_cact + ci];
     if (!mask) continue;
     int b1 = wi[L.i_cb1 + ci], b2 = wi[L.i_cb2 + ci], t1 = wi[L.i_ct1 + ci], t2 = wi[L.i_ct2 + ci];
-    if (!((t1 >= 0 && tcoupled[t1]) || (t2 >= 0 && tcoupled[t2]))) continue;
+    const bool c1 = t1 >= 0 && tcoupled[t1], c2 = t2 >= 0 && tcoupled[t2];
+    if (!(c1 || c2)) continue;
+    if (GE_NW > 1 && island_owner(island, c1 ? t1 : t2) != wid) continue;
     const double* c = ws + L.con + ci * L.cstride;
     int dim = wi[L.i_cdim + ci];
     int i1 = m.body_lastdof[b1], i2 = m.body_lastdof[b2], n = 0, mydof = -1, minE = 0x7fffffff;
@@ -185,12 +193,12 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
     while (i1 != i2) {
       int e; double s;
       if (i2 > i1) { e = i2; s = 1.0; i2 = m.dof_parentid[i2]; } else { e = i1; s = -1.0; i1 = m.dof_parentid[i1]; }
-      if (n == lane) { mydof = e; mysgn = s; }
+      if (n == wl) { mydof = e; mysgn = s; }
       if (e < minE) minE = e;
       n++;
     }
     double J[6] = {0, 0, 0, 0, 0, 0}, t[6] = {0, 0, 0, 0, 0, 0};
-    if (lane < n) {
+    if (wl < n) {
       jac_column(c, dim, cdof + 6 * mydof, mysgn, J);
       weight_column(c, dim, mask, J, t);
     }
@@ -198,15 +206,17 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
       int dj = __shfl_sync(FULL, mydof, j);
       double h = 0;
       for (int k = 0; k < dim; k++) h += t[k] * __shfl_sync(FULL, J[k], j);
-      if (lane < n && mydof >= dj) H[HIDX(mydof, dj)] += h;
+      if (wl < n && mydof >= dj) H[HIDX(mydof, dj)] += h;
     }
     __syncwarp();
   }
-  if (lane == 0)
+  if (wl == 0)
     for (int i = 0; i < nsr; i++) {
       if (!wi[L.i_sract + i]) continue;
       int A = wi[L.i_srA + i], B = wi[L.i_srB + i];
-      if (!tcoupled[m.dof_treeindex[A]]) continue;
+      const int tA = m.dof_treeindex[A];
+      if (!tcoupled[tA]) continue;
+      if (GE_NW > 1 && island_owner(island, tA) != wid) continue;
       double D = srv(ws, SR_D, i), ca = srv(ws, SR_CA, i), cb = srv(ws, SR_CB, i);
       H[HIDX(A, A)] += D * ca * ca;
       if (B >= 0) {
@@ -215,7 +225,7 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
         H[HIDX(hi, lo)] += D * ca * cb;
       }
     }
-  __syncwarp();
+  gsync();
 }
 
 // Dense Cholesky + forward/backward substitution of one tree block (rows lo .. lo+nt-1 of the packed matrix, nt <= GE_GROUP)
@@ -224,21 +234,20 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
 // (the factor is used exactly once).  Rows l >= nt are padded with the identity.  x[row] := sign * (H_block^-1 g)[row].
 // (r02: the shared-memory version spent ~1000 instructions per block in packed-index arithmetic, LDS/STS and three __syncwarp per
 // column; mass_block_solve + the group path of cholesky_solve were 22 % of k_run's time.)
-__device__ __forceinline__ void group_chol_solve(const double* H, int lo, int nt, int l, unsigned gmask, const double* g_, double* x, double sign) {
+__device__ __noinline__ void group_chol_solve(const double* H, int lo, int nt, int l, unsigned gmask, const double* g_, double* x, double sign) {
   const int row = lo + l;
   const bool mine = l < nt;
   double r[GE_GROUP], inv[GE_GROUP];
 #pragma unroll
   for (int j = 0; j < GE_GROUP; j++) r[j] = (mine && j <= l) ? H[HIDX(row, lo + j)] : (j == l ? 1.0 : 0.0);
-  // right-looking Cholesky: after step j, r[j] holds L[l][j] (rows l >= j), later columns carry the Schur complement
+  // right-looking Cholesky: after step j, r[j] holds L[l][j] (rows l > j), later columns carry the Schur complement.  Only 1 / L[j][j]
+  // is ever needed (scaling of column j, the two substitutions), so the pivot is one reciprocal square root (rsqrt: <= 1 ulp).
 #pragma unroll
   for (int j = 0; j < GE_GROUP; j++) {
     double d = __shfl_sync(gmask, r[j], j, GE_GROUP);
     if (d < GE_MINVAL) d = GE_MINVAL;
-    const double ljj = sqrt(d);
-    inv[j] = 1.0 / ljj;
+    inv[j] = rsqrt(d);
     if (l > j) r[j] *= inv[j];
-    else if (l == j) r[j] = ljj;
 #pragma unroll
     for (int k = j + 1; k < GE_GROUP; k++) {
       const double lkj = __shfl_sync(gmask, r[j], k, GE_GROUP);  // L[k][j]
@@ -280,76 +289,77 @@ __device__ __noinline__ bool mass_block_solve(double* ws, double* x, double hdam
   // "simple" trees (free-floating single bodies): the block is a model constant, multiply by the precomputed inverse
   // (tree_Minv[t][0] = M^-1, [1] = (M + h*damping)^-1 for h = opt.timestep); rows are read before any is written
   const int which = hdamp != 0.0 ? 1 : 0;
-  double xs[2] = {0, 0};
-  {
-    int n = 0;
-    LANE_LOOP(i, m.nv) {
-      int t = m.dof_treeindex[i];
-      if (m.tree_simple[t]) {
-        int lo = m.tree_dofadr[t];
-        const double* Mi = m.tree_Minv + ((size_t)(t * 2 + which) * 6 + (i - lo)) * 6;
-        double s = 0;
-        for (int j = 0; j < 6; j++) s += Mi[j] * x[lo + j];
-        xs[n] = s;
-      }
-      n++;
+  double* tmp = ws + L.Mv;  // free dof vector in both callers (before the Newton solve / after it)
+  LANE_LOOP(i, m.nv) {
+    int t = m.dof_treeindex[i];
+    if (m.tree_simple[t]) {
+      int lo = m.tree_dofadr[t];
+      const double* Mi = m.tree_Minv + ((size_t)(t * 2 + which) * 6 + (i - lo)) * 6;
+      double s = 0;
+#pragma unroll
+      for (int j = 0; j < 6; j++) s += Mi[j] * x[lo + j];
+      tmp[i] = s;
+    } else {
+      int root = m.tree_dofadr[t];
+      for (int j = root; j <= i; j++) H[HIDX(i, j)] = 0;
+      int a = m.dof_Madr[i], k = 0;
+      for (int j = i; j >= 0; j = m.dof_parentid[j], k++) H[HIDX(i, j)] = qM[a + k];
+      if (hdamp != 0.0) H[HIDX(i, i)] += hdamp * m.dof_damping[i];
     }
   }
-  LANE_LOOP(i, m.nv) {
-    if (m.tree_simple[m.dof_treeindex[i]]) continue;
-    int root = m.tree_dofadr[m.dof_treeindex[i]];
-    for (int j = root; j <= i; j++) H[HIDX(i, j)] = 0;
-    int a = m.dof_Madr[i], k = 0;
-    for (int j = i; j >= 0; j = m.dof_parentid[j], k++) H[HIDX(i, j)] = qM[a + k];
-    if (hdamp != 0.0) H[HIDX(i, i)] += hdamp * m.dof_damping[i];
-  }
-  __syncwarp();
-  {
-    int n = 0;
-    LANE_LOOP(i, m.nv) { if (m.tree_simple[m.dof_treeindex[i]]) x[i] = xs[n]; n++; }
-  }
+  gsync();
+  LANE_LOOP(i, m.nv) if (m.tree_simple[m.dof_treeindex[i]]) x[i] = tmp[i];
   const int g = lane / GE_GROUP, l = lane % GE_GROUP;
-  const unsigned gmask = ((1u << GE_GROUP) - 1u) << (g * GE_GROUP);
-  // the remaining trees, packed four at a time onto the lane groups
+  const unsigned gmask = ((1u << GE_GROUP) - 1u) << (((lane & 31) / GE_GROUP) * GE_GROUP);
+  // the remaining trees, packed GE_LANES / 8 at a time onto the lane groups
   int slot = 0;
   for (int t = 0; t < m.ntree; t++) {
     if (m.tree_simple[t]) continue;
-    if (slot % (32 / GE_GROUP) == g) group_chol_solve(H, m.tree_dofadr[t], m.tree_dofnum[t], l, gmask, x, x, 1.0);
+    if (slot % (GE_LANES / GE_GROUP) == g) group_chol_solve(H, m.tree_dofadr[t], m.tree_dofnum[t], l, gmask, x, x, 1.0);
     slot++;
   }
-  __syncwarp();
+  gsync();
   return true;
 }
 
 // x := -H^-1 g.  Uncoupled trees: 8-lane groups (group_chol_solve).  Coupled trees: right-looking dense Cholesky per island with
-// the whole warp (each lane owns rows lane, lane+32, ... of the island's dof list).
+// one whole warp (each lane owns rows lane, lane+32, ... of the island's dof list); the warps of a CTA-per-env build take the
+// islands they own (island_owner) concurrently.
 __device__ __noinline__ void cholesky_solve(double* ws, int* wi, double* x, const double* g_, int lane) {
   const DevModel& m = c_m; const Layout& L = c_L;
   double* H = ws + L.H;
+  const int wl = lane & 31, wid = lane >> 5;
   const int* tcoupled = wi + L.i_tcoupled;
   bool any_coupled = false;
   for (int t = 0; t < m.ntree; t++) any_coupled |= tcoupled[t] != 0;
   {
     const int g = lane / GE_GROUP, l = lane % GE_GROUP;
-    const unsigned gmask = ((1u << GE_GROUP) - 1u) << (g * GE_GROUP);
-    for (int t0 = 0; t0 < m.ntree; t0 += 32 / GE_GROUP) {
+    const unsigned gmask = ((1u << GE_GROUP) - 1u) << ((wl / GE_GROUP) * GE_GROUP);
+    for (int t0 = 0; t0 < m.ntree; t0 += GE_LANES / GE_GROUP) {
       int t = t0 + g;
       if (t >= m.ntree || tcoupled[t]) continue;  // group-uniform
       group_chol_solve(H, m.tree_dofadr[t], m.tree_dofnum[t], l, gmask, g_, x, -1.0);
     }
   }
-  __syncwarp();
+  gsync();
   if (!any_coupled) return;
-  // coupled trees: one dense Cholesky per island over the island's dof list (ascending), rows spread over the lanes
+  // coupled trees: one dense Cholesky per island over the island's dof list (ascending), rows spread over the lanes of the owner warp.
+  // The dof lists of the islands are laid out one after the other in the int scratch (the islands partition the coupled trees).
   const int* island = wi + L.i_island;
-  int* idx = (int*)wi + L.i_first;  // (the row-envelope array of the skyline version; free here)
+  int* idx_all = (int*)wi + L.i_first;  // (the row-envelope array of the skyline version; free here)
+  int idx_off = 0;
   for (int rep = 0; rep < m.ntree; rep++) {
     if (!tcoupled[rep] || island[rep] != rep) continue;
     int n = 0;
+    for (int t = rep; t < m.ntree; t++) if (tcoupled[t] && island[t] == rep) n += m.tree_dofnum[t];
+    int* idx = idx_all + idx_off;
+    idx_off += n;
+    if (GE_NW > 1 && island_owner(island, rep) != wid) continue;
+    n = 0;
     for (int t = rep; t < m.ntree; t++) {
       if (!tcoupled[t] || island[t] != rep) continue;
       int lo = m.tree_dofadr[t], nt = m.tree_dofnum[t];
-      LANE_LOOP(k, nt) idx[n + k] = lo + k;
+      for (int k = wl; k < nt; k += 32) idx[n + k] = lo + k;
       n += nt;
     }
     __syncwarp();
@@ -359,10 +369,10 @@ __device__ __noinline__ void cholesky_solve(double* ws, int* wi, double* x, cons
       if (d < GE_MINVAL) d = GE_MINVAL;
       double ljj = sqrt(d), inv = 1.0 / ljj;
       __syncwarp();
-      for (int ii = jj + 1 + lane; ii < n; ii += 32) H[HIDX(idx[ii], j)] *= inv;
-      if (lane == 0) H[HIDX(j, j)] = ljj;
+      for (int ii = jj + 1 + wl; ii < n; ii += 32) H[HIDX(idx[ii], j)] *= inv;
+      if (wl == 0) H[HIDX(j, j)] = ljj;
       __syncwarp();
-      for (int ii = jj + 1 + lane; ii < n; ii += 32) {
+      for (int ii = jj + 1 + wl; ii < n; ii += 32) {
         const int i = idx[ii];
         double lij = H[HIDX(i, j)];
         if (lij == 0.0) continue;
@@ -370,27 +380,28 @@ __device__ __noinline__ void cholesky_solve(double* ws, int* wi, double* x, cons
       }
       __syncwarp();
     }
-    LANE_LOOP(ii, n) x[idx[ii]] = g_[idx[ii]];
+    for (int ii = wl; ii < n; ii += 32) x[idx[ii]] = g_[idx[ii]];
     __syncwarp();
     for (int jj = 0; jj < n; jj++) {  // L y = g, column oriented
       const int j = idx[jj];
       double yj = x[j] / H[HIDX(j, j)];
       __syncwarp();
-      if (lane == 0) x[j] = yj;
-      for (int ii = jj + 1 + lane; ii < n; ii += 32) x[idx[ii]] -= H[HIDX(idx[ii], j)] * yj;
+      if (wl == 0) x[j] = yj;
+      for (int ii = jj + 1 + wl; ii < n; ii += 32) x[idx[ii]] -= H[HIDX(idx[ii], j)] * yj;
       __syncwarp();
     }
     for (int ii = n - 1; ii >= 0; ii--) {  // L^T x = y, column oriented
       const int i = idx[ii];
       double xi = x[i] / H[HIDX(i, i)];
       __syncwarp();
-      if (lane == 0) x[i] = xi;
-      for (int kk = lane; kk < ii; kk += 32) x[idx[kk]] -= H[HIDX(i, idx[kk])] * xi;
+      if (wl == 0) x[i] = xi;
+      for (int kk = wl; kk < ii; kk += 32) x[idx[kk]] -= H[HIDX(i, idx[kk])] * xi;
       __syncwarp();
     }
-    LANE_LOOP(ii, n) x[idx[ii]] = -x[idx[ii]];
+    for (int ii = wl; ii < n; ii += 32) x[idx[ii]] = -x[idx[ii]];
     __syncwarp();
   }
+  gsync();
 }
 
 }  // namespace ge

@@ -108,6 +108,76 @@ __device__ __forceinline__ double warp_max(double v) {
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
   return v;
 }
+// ---- primitives over the GE_LANES threads that share one environment (ge_variant.h): a warp, or a CTA of GE_NW warps
+#ifndef GE_LANES
+#define GE_LANES 32
+#define GE_NW 1
+#endif
+#if GE_NW == 1
+__device__ __forceinline__ void gsync() { __syncwarp(); }
+__device__ __forceinline__ double group_sum(double v) { return warp_sum(v); }
+__device__ __forceinline__ double group_max(double v) { return warp_max(v); }
+__device__ __forceinline__ bool group_any(bool p) { return __any_sync(FULL, p) != 0; }
+__device__ __forceinline__ int group_bcast_int(int v, int lane) { return __shfl_sync(FULL, v, 0); }
+// exclusive prefix of one int per thread in thread order, and the total (ordered compaction)
+__device__ __forceinline__ int group_exscan(int v, int lane, int& total) {
+  int off = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(FULL, off, o); if (lane >= o) off += u; }
+  total = __shfl_sync(FULL, off, 31);
+  return off - v;
+}
+#else
+__device__ __forceinline__ void gsync() { __syncthreads(); }
+// fixed order: butterfly inside each warp, then warp 0 .. GE_NW-1 (deterministic)
+__device__ __forceinline__ double group_sum(double v) {
+  __shared__ double red[GE_NW];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = red[0];
+#pragma unroll
+  for (int w = 1; w < GE_NW; w++) s += red[w];
+  __syncthreads();
+  return s;
+}
+__device__ __forceinline__ double group_max(double v) {
+  __shared__ double red[GE_NW];
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = red[0];
+#pragma unroll
+  for (int w = 1; w < GE_NW; w++) s = fmax(s, red[w]);
+  __syncthreads();
+  return s;
+}
+__device__ __forceinline__ bool group_any(bool p) { return __syncthreads_or(p ? 1 : 0) != 0; }
+__device__ __forceinline__ int group_bcast_int(int v, int lane) {
+  __shared__ int b;
+  if (lane == 0) b = v;
+  __syncthreads();
+  int r = b;
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ int group_exscan(int v, int lane, int& total) {
+  __shared__ int wsum[GE_NW];
+  const int wl = lane & 31, wid = lane >> 5;
+  int off = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(FULL, off, o); if (wl >= o) off += u; }
+  if (wl == 31) wsum[wid] = off;
+  __syncthreads();
+  int before = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < GE_NW; w++) { if (w < wid) before += wsum[w]; tot += wsum[w]; }
+  __syncthreads();
+  total = tot;
+  return before + off - v;
+}
+#endif
+
 // argmax with lowest-index tie break; returns the winning (value, index) on every lane
 __device__ __forceinline__ void warp_argmax(double& v, int& idx) {
 #pragma unroll

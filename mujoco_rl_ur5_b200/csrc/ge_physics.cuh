@@ -15,7 +15,7 @@ namespace ge {
 __constant__ DevModel c_m;
 __constant__ Layout c_L;
 
-#define LANE_LOOP(i, n) for (int i = lane; i < (n); i += 32)
+#define LANE_LOOP(i, n) for (int i = lane; i < (n); i += GE_LANES)
 
 // ------------------------------------------------------------------------------------------------ kinematics
 // Three lane-parallel phases, no level synchronisation: (1) every body's transform relative to its parent,
@@ -57,7 +57,7 @@ __device__ __noinline__ void stage_fk(double* ws, int lane) {
     v3copy(lpos + 3 * b, pos);
     for (int c = 0; c < 4; c++) lquat[4 * b + c] = quat[c];
   }
-  __syncwarp();
+  gsync();
   double *xpos = ws + L.xpos, *xmat = ws + L.xmat;
   LANE_LOOP(b, m.nbody) {
     double pos[3], quat[4], t[3], nq[4];
@@ -74,7 +74,7 @@ __device__ __noinline__ void stage_fk(double* ws, int lane) {
     q2mat(R, quat);
     for (int c = 0; c < 9; c++) xmat[9 * b + c] = R[c];
   }
-  __syncwarp();
+  gsync();
   double* cdof = ws + L.cdof;
   LANE_LOOP(d, m.nv) {
     int j = m.dof_jntid[d], b = m.dof_bodyid[d], k = d - m.jnt_dofadr[j], type = m.jnt_type[j], p = m.body_parentid[b];
@@ -90,7 +90,7 @@ __device__ __noinline__ void stage_fk(double* ws, int lane) {
     if (type == J_SLIDE) { v3set(c, 0, 0, 0); v3copy(c + 3, ax); }
     else { v3copy(c, ax); v3cross(c + 3, an, ax); }
   }
-  __syncwarp();  // the local joint frames (janchor, jaxis) are dead from here on: cinert overwrites them
+  gsync();  // the local joint frames (janchor, jaxis) are dead from here on: cinert overwrites them
   double* cinert = ws + L.cinert;
   LANE_LOOP(b, m.nbody) {
     double* I = cinert + 10 * b;
@@ -115,7 +115,7 @@ __device__ __noinline__ void stage_fk(double* ws, int lane) {
     m3mul(gmat + 9 * g, xmat + 9 * b, m.geom_lmat + 9 * g);
     m3mulv(t, gmat + 9 * g, m.geom_obbcenter + 3 * g); v3add(ws + L.gcen + 3 * g, gpos + 3 * g, t);  // bounding-sphere / OBB centre
   }
-  __syncwarp();
+  gsync();
 }
 
 // ------------------------------------------------------------------------------------------------ bias forces (RNE) -> ws[qfrc_smooth] := qfrc_bias
@@ -136,7 +136,7 @@ __device__ __noinline__ void stage_rne(double* ws, int lane) {
     }
     cross_motion(out, v, cdof + 6 * d);
   }
-  __syncwarp();
+  gsync();
   LANE_LOOP(b, m.nbody) {
     double v[6] = {0, 0, 0, 0, 0, 0}, a[6] = {0, 0, 0, -m.gravity[0], -m.gravity[1], -m.gravity[2]};
     for (int d = m.body_lastdof[b]; d >= 0; d = m.dof_parentid[d]) {
@@ -147,17 +147,17 @@ __device__ __noinline__ void stage_rne(double* ws, int lane) {
     inert_mul(Ia, cinert + 10 * b, a); inert_mul(Iv, cinert + 10 * b, v); cross_force(x, v, Iv);
     for (int c = 0; c < 6; c++) { cvel[6 * b + c] = v[c]; cfrc[6 * b + c] = Ia[c] + x[c]; }
   }
-  __syncwarp();
+  gsync();
   LANE_LOOP(b, m.nbody) {  // subtree sums: depth-first numbering makes a subtree a contiguous range
     double s[6] = {0, 0, 0, 0, 0, 0};
     int n = m.body_subtreenum[b];
     for (int c2 = b; c2 < b + n; c2++) for (int c = 0; c < 6; c++) s[c] += cfrc[6 * c2 + c];
     for (int c = 0; c < 6; c++) cacc[6 * b + c] = s[c];
   }
-  __syncwarp();
+  gsync();
   double* bias = ws + L.qfrc_smooth;
   LANE_LOOP(d, m.nv) bias[d] = dot6(cdof + 6 * d, cacc + 6 * m.dof_bodyid[d]);
-  __syncwarp();
+  gsync();
 }
 
 // ------------------------------------------------------------------------------------------------ CRBA -> qM (tree-sparse rows: self, parent, grandparent, ...)
@@ -172,7 +172,7 @@ __device__ __noinline__ void stage_crb(double* ws, int lane) {
     for (int c2 = b; c2 < b + n; c2++) for (int c = 0; c < 10; c++) s[c] += cinert[10 * c2 + c];
     for (int c = 0; c < 10; c++) crb[10 * b + c] = s[c];
   }
-  __syncwarp();
+  gsync();
   LANE_LOOP(i, m.nv) {
     double f[6];
     inert_mul(f, crb + 10 * m.dof_bodyid[i], cdof + 6 * i);
@@ -180,7 +180,7 @@ __device__ __noinline__ void stage_crb(double* ws, int lane) {
     qM[adr] = dot6(cdof + 6 * i, f) + m.dof_armature[i];
     for (int j = m.dof_parentid[i]; j >= 0; j = m.dof_parentid[j], k++) qM[adr + k] = dot6(cdof + 6 * j, f);
   }
-  __syncwarp();
+  gsync();
 }
 
 // L^T D L factorisation / solve of the tree-sparse mass matrix; one lane per kinematic tree (trees are independent)
@@ -199,7 +199,7 @@ __device__ __noinline__ void factor_trees(double* LD, int lane) {
       }
     }
   }
-  __syncwarp();
+  gsync();
 }
 __device__ __noinline__ void solve_trees(const double* LD, double* x, int lane) {
   const DevModel& m = c_m;
@@ -218,7 +218,7 @@ __device__ __noinline__ void solve_trees(const double* LD, double* x, int lane) 
       x[k] = xk;
     }
   }
-  __syncwarp();
+  gsync();
 }
 // r = M v, one lane per dof (ancestors from the dof's own row, descendants from theirs)
 __device__ __noinline__ void mul_M(const double* qM, double* r, const double* v, int lane) {
@@ -231,7 +231,7 @@ __device__ __noinline__ void mul_M(const double* qM, double* r, const double* v,
     for (int c = i + 1; c < i + n; c++) s += qM[m.dof_Madr[c] + m.dof_depth[c] - di] * v[c];
     r[i] = s;
   }
-  __syncwarp();
+  gsync();
 }
 
 // ------------------------------------------------------------------------------------------------ collision
@@ -722,14 +722,20 @@ __device__ __forceinline__ void make_frame(double* fr) {
 }
 
 // Broad phase over the static candidate pair list (bounding spheres, then oriented boxes), analytic narrow phase one lane
-// per surviving pair, then the MPR pairs one after the other with the whole warp.  Returns the number of contacts; sets
-// bit 0 of *status on overflow.  (The oracle emits contacts in the same order: analytic pairs first, then MPR pairs.)
+// per surviving pair, then the MPR pairs, each with one whole warp (the warps of a CTA-per-env build take them round-robin).
+// Returns the number of contacts; sets bit 0 of *status on overflow.  (The oracle emits contacts in the same order: analytic
+// pairs first, then MPR pairs, both in candidate order.)
+__device__ __forceinline__ bool pair_is_analytic(int t1, int t2) {
+  return (t1 == G_PLANE) || (t1 == G_SPHERE && (t2 == G_SPHERE || t2 == G_BOX || t2 == G_CAPSULE || t2 == G_CYLINDER)) ||
+         (t1 == G_BOX && t2 == G_BOX) || (t1 == G_CAPSULE && t2 == G_CAPSULE);
+}
 __device__ __noinline__ int stage_collision(double* ws, int* wi, int lane, int* status) {
   const DevModel& m = c_m; const Layout& L = c_L;
   const double *gpos = ws + L.gpos, *gmat = ws + L.gmat, *gcen = ws + L.gcen;
+  const int wl = lane & 31, wid = lane >> 5;
   int* cand = wi + L.i_cand;
   int ncand = 0;
-  for (int base = 0; base < m.npair; base += 32) {
+  for (int base = 0; base < m.npair; base += GE_LANES) {
     int p = base + lane;
     bool pass = false;
     if (p < m.npair) {
@@ -752,20 +758,18 @@ __device__ __noinline__ int stage_collision(double* ws, int* wi, int lane, int* 
           pass = !obb_separated(c1, gmat + 9 * g1, m.geom_obbhalf + 3 * g1, c2, gmat + 9 * g2, m.geom_obbhalf + 3 * g2, m.pair_margin[p]);
       }
     }
-    unsigned mask = __ballot_sync(FULL, pass);
-    if (pass) {
-      int pos = ncand + __popc(mask & ((1u << lane) - 1));
-      if (pos < L.maxcand) cand[pos] = p;
-    }
-    ncand += __popc(mask);
+    int total;
+    int pos = ncand + group_exscan(pass ? 1 : 0, lane, total);
+    if (pass && pos < L.maxcand) cand[pos] = p;
+    ncand += total;
   }
   if (ncand > L.maxcand) { ncand = L.maxcand; *status |= 1; }
-  __syncwarp();
+  gsync();
   double* con = ws + L.con;
   int *cb1 = wi + L.i_cb1, *cb2 = wi + L.i_cb2, *cdim = wi + L.i_cdim, *cpair = wi + L.i_cpair;
   int ncon = 0;
   // ---- analytic pairs
-  for (int base = 0; base < ncand; base += 32) {
+  for (int base = 0; base < ncand; base += GE_LANES) {
     int ci = base + lane;
     PairContacts pc;
     pc.n = 0;
@@ -788,11 +792,8 @@ __device__ __noinline__ int stage_collision(double* ws, int* wi, int lane, int* 
       else if (t1 == G_CAPSULE && t2 == G_CAPSULE) col_capsule_capsule(ws, g1, g2, margin, pc);
     }
     // ordered compaction of the per-lane contact lists
-    int off = pc.n;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, off, o); if (lane >= o) off += v; }
-    int total = __shfl_sync(FULL, off, 31);
-    off = ncon + off - pc.n;
+    int total;
+    int off = ncon + group_exscan(pc.n, lane, total);
     for (int k = 0; k < pc.n; k++) {
       int idx = off + k;
       if (idx >= L.maxcon) break;
@@ -803,14 +804,13 @@ __device__ __noinline__ int stage_collision(double* ws, int* wi, int lane, int* 
     ncon += total;
   }
   if (ncon > L.maxcon) { ncon = L.maxcon; *status |= 1; }
-  __syncwarp();
+  gsync();
   // ---- convex pairs through MPR
+#if GE_NW == 1
   for (int ci = 0; ci < ncand; ci++) {
     int p = cand[ci];
     int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1], t1 = m.geom_type[g1], t2 = m.geom_type[g2];
-    bool analytic = (t1 == G_PLANE) || (t1 == G_SPHERE && (t2 == G_SPHERE || t2 == G_BOX || t2 == G_CAPSULE || t2 == G_CYLINDER)) ||
-                    (t1 == G_BOX && t2 == G_BOX) || (t1 == G_CAPSULE && t2 == G_CAPSULE);
-    if (analytic) continue;
+    if (pair_is_analytic(t1, t2)) continue;
     double margin = m.pair_margin[p], depth, dir[3], pos[3];
     if (!mpr_w(ws, g1, g2, 0.5 * margin, &depth, dir, pos, lane)) continue;
     double dist = margin - depth;
@@ -823,7 +823,51 @@ __device__ __noinline__ int stage_collision(double* ws, int* wi, int lane, int* 
     }
     ncon++;
   }
-  __syncwarp();
+  gsync();
+#else
+  {
+    // every warp walks the whole candidate list and takes the MPR pairs k = wid, wid + GE_NW, ...; MPR pair number k writes its
+    // result into contact slot ncon + k (cpair = -1: no contact), then the slots are compacted in order
+    int k = 0;
+    bool overflow = false;
+    for (int ci = 0; ci < ncand; ci++) {
+      int p = cand[ci];
+      int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1], t1 = m.geom_type[g1], t2 = m.geom_type[g2];
+      if (pair_is_analytic(t1, t2)) continue;
+      const int slot = ncon + k;
+      const bool mine = (k % GE_NW) == wid;
+      k++;
+      if (slot >= L.maxcon) { overflow = true; continue; }
+      if (!mine) continue;
+      double margin = m.pair_margin[p], depth = 0, dir[3], pos[3];
+      bool hit = mpr_w(ws, g1, g2, 0.5 * margin, &depth, dir, pos, wl);
+      double dist = margin - depth;
+      if (hit && dist >= margin) hit = false;
+      if (wl == 0) {
+        double* c = con + slot * L.cstride;
+        if (hit) { c[C_DIST] = dist; v3copy(c + C_POS, pos); v3copy(c + C_FRAME, dir); }
+        cpair[slot] = hit ? p : -1;
+      }
+    }
+    gsync();
+    int nslots = ncon + k < L.maxcon ? ncon + k : L.maxcon;
+    // stable in-place compaction by warp 0: record j moves down to the next free slot (never overtakes an unread record)
+    int out = ncon;
+    for (int j = ncon; j < nslots; j++) {
+      int p = cpair[j];
+      if (p < 0) continue;
+      if (out != j && wid == 0) {
+        for (int q = wl; q < C_FRAME + 3; q += 32) con[out * L.cstride + q] = con[j * L.cstride + q];
+        if (wl == 0) cpair[out] = p;
+      }
+      out++;
+      gsync();
+    }
+    if (overflow) *status |= 1;
+    ncon = out;
+    gsync();
+  }
+#endif
   // ---- per-contact frame and solver parameters
   LANE_LOOP(i, ncon) {
     double* c = con + i * L.cstride;
@@ -854,7 +898,7 @@ __device__ __noinline__ int stage_collision(double* ws, int* wi, int lane, int* 
     if (dim > 1) { R = 2 * mu[0] * mu[0] / m.impratio * R; if (R < GE_MINVAL) R = GE_MINVAL; }
     c[C_D] = 1.0 / R; c[C_B] = B; c[C_KR] = K * imp * (dist - margin);
   }
-  __syncwarp();
+  gsync();
   return ncon;
 }
 

@@ -16,14 +16,14 @@ struct RenderCtx { double* gframes; size_t cap_envs; };
 static inline void render_init(RenderCtx& r, const DevModel&, const char*) { r.gframes = nullptr; r.cap_envs = 0; }
 static inline void render_free(RenderCtx& r) { if (r.gframes) cudaFree(r.gframes); r.gframes = nullptr; }
 
-__global__ void __launch_bounds__(32) k_render_fk(const double* qpos, int n_env, double* gframes) {
+__global__ void __launch_bounds__(GE_LANES) k_render_fk(const double* qpos, int n_env, double* gframes) {
   extern __shared__ double smem[];
   const DevModel& m = c_m; const Layout& L = c_L;
   int env = blockIdx.x, lane = threadIdx.x;
   if (env >= n_env) return;
   double* ws = smem;
   LANE_LOOP(i, m.nq) ws[L.qpos + i] = qpos[(size_t)env * m.nq + i];
-  __syncwarp();
+  gsync();
   stage_fk(ws, lane);
   double* out = gframes + (size_t)env * m.ngeom * 12;
   LANE_LOOP(g, m.ngeom) {
@@ -215,7 +215,7 @@ static inline int render_launch(RenderCtx& rc, const DevModel& m, const Layout& 
   }
   static bool attr_done = false;
   if (!attr_done && L.fk_bytes > 48 * 1024) { cudaFuncSetAttribute(k_render_fk, cudaFuncAttributeMaxDynamicSharedMemorySize, L.fk_bytes); attr_done = true; }
-  k_render_fk<<<n_env, 32, L.fk_bytes, stream>>>(qpos, n_env, rc.gframes);
+  k_render_fk<<<n_env, GE_LANES, L.fk_bytes, stream>>>(qpos, n_env, rc.gframes);
   int tiles = ((W + RTILE - 1) / RTILE) * ((H + RTILE - 1) / RTILE);
   dim3 grid(tiles, n_env), blk(RTILE, RTILE);
   k_render<<<grid, blk, 0, stream>>>(rc.gframes, n_env, cam, W, H, rgb, depth);

@@ -49,7 +49,7 @@ __device__ __noinline__ void body_vel(double* ws, const double* x, int lane) {
     }
     for (int c = 0; c < 6; c++) Vb[6 * b + c] = v[c];
   }
-  __syncwarp();
+  gsync();
 }
 // base rows of every contact applied to the current V_b: out slot `slot` (offset inside the contact record)
 __device__ __noinline__ void contact_base(double* ws, const int* wi, int ncon, int slot, int lane) {
@@ -99,7 +99,7 @@ __device__ __noinline__ int stage_constraints(double* ws, int* wi, int lane, int
     srv(ws, SR_CA, i) = 1; srv(ws, SR_CB, i) = -deriv; srv(ws, SR_D, i) = 1.0 / R; srv(ws, SR_AREF, i) = -B * vel - K * imp * pos;
   }
   nsr = m.neq;
-  for (int base = 0; base < m.njnt; base += 32) {  // joint limits, ordered compaction (joint order, lower side first)
+  for (int base = 0; base < m.njnt; base += GE_LANES) {  // joint limits, ordered compaction (joint order, lower side first)
     int j = base + lane, cnt = 0;
     double dist[2];
     if (j < m.njnt && m.jnt_limited[j]) {
@@ -107,11 +107,8 @@ __device__ __noinline__ int stage_constraints(double* ws, int* wi, int lane, int
       dist[0] = q - m.jnt_range[2 * j]; dist[1] = m.jnt_range[2 * j + 1] - q;
       cnt = (dist[0] < mg) + (dist[1] < mg);
     }
-    int off = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, off, o); if (lane >= o) off += v; }
-    int total = __shfl_sync(FULL, off, 31);
-    off = nsr + off - cnt;
+    int total;
+    int off = nsr + group_exscan(cnt, lane, total);
     if (cnt) {
       double mg = m.jnt_margin[j];
       int d = m.jnt_dofadr[j];
@@ -133,7 +130,7 @@ __device__ __noinline__ int stage_constraints(double* ws, int* wi, int lane, int
   if (nsr > GE_MAXSR) { nsr = GE_MAXSR; *status |= 1; }
   body_vel(ws, qvel, lane);
   contact_base(ws, wi, ncon, c_vel(), lane);
-  __syncwarp();
+  gsync();
   return nsr;
 }
 
@@ -176,8 +173,8 @@ __device__ __noinline__ double nt_update(double* ws, int* wi, int ncon, int nsr,
     srv(ws, SR_JV, i) = act ? -D * x : 0.0;
     if (act) cost += 0.5 * D * x * x;
   }
-  cost = warp_sum(cost);
-  __syncwarp();
+  cost = group_sum(cost);
+  gsync();
   // J^T f: one lane per contact forms the contact wrench about the world origin once (scratch: the Hessian storage, free
   // between two Newton directions), one lane per body then adds the wrenches of its contacts in contact order
   double *Wb = ws + L.Wb, *Wsub = ws + L.Vb, *Wc = ws + L.H;
@@ -190,7 +187,7 @@ __device__ __noinline__ double nt_update(double* ws, int* wi, int ncon, int nsr,
     v3cross(tq, c + C_POS, f); v3add(tq, tq, tr);
     for (int k = 0; k < 3; k++) { Wc[6 * i + k] = tq[k]; Wc[6 * i + 3 + k] = f[k]; }
   }
-  __syncwarp();
+  gsync();
   LANE_LOOP(b, m.nbody) {
     double w[6] = {0, 0, 0, 0, 0, 0};
     if (m.body_lastdof[b] >= 0)
@@ -201,14 +198,14 @@ __device__ __noinline__ double nt_update(double* ws, int* wi, int ncon, int nsr,
       }
     for (int k = 0; k < 6; k++) Wb[6 * b + k] = w[k];
   }
-  __syncwarp();
+  gsync();
   LANE_LOOP(b, m.nbody) {
     double s[6] = {0, 0, 0, 0, 0, 0};
     int n = m.body_subtreenum[b];
     for (int c2 = b; c2 < b + n; c2++) for (int k = 0; k < 6; k++) s[k] += Wb[6 * c2 + k];
     for (int k = 0; k < 6; k++) Wsub[6 * b + k] = s[k];
   }
-  __syncwarp();
+  gsync();
   double* qfc = ws + L.qfrc_constraint;
   const double* cdof = ws + L.cdof;
   LANE_LOOP(d, m.nv) {
@@ -220,7 +217,7 @@ __device__ __noinline__ double nt_update(double* ws, int* wi, int ncon, int nsr,
     }
     qfc[d] = s;
   }
-  __syncwarp();
+  gsync();
   return cost;
 }
 
@@ -237,7 +234,7 @@ __device__ __noinline__ double rows_cost(double* ws, const int* wi, int ncon, in
     double x = srv(ws, field, i) - srv(ws, SR_AREF, i);
     if (wi[L.i_srtype + i] == 0 || x < 0) cost += 0.5 * srv(ws, SR_D, i) * x * x;
   }
-  return warp_sum(cost);
+  return group_sum(cost);
 }
 
 }  // namespace ge
@@ -258,37 +255,37 @@ __device__ __noinline__ int solve_newton(double* ws, int* wi, int lane, int ncon
   const double* qM = ws + L.qM;
   const int ja = c_ja(), jv = c_jv();
   LANE_LOOP(d, nv) { qacc[d] = qacc_smooth[d]; qfc[d] = 0; }
-  __syncwarp();
+  gsync();
   if (ncon + nsr == 0) { for (int k = 0; k < GE_NEWTON_BARRIERS; k++) newton_barrier(sync); return 0; }
   // warm start choice
   LANE_LOOP(d, nv) grad[d] = qaccws[d] - qacc_smooth[d];
-  __syncwarp();
+  gsync();
   mul_M(qM, Mv, grad, lane);
   double gws = 0;
   LANE_LOOP(d, nv) gws += 0.5 * grad[d] * Mv[d];
-  gws = warp_sum(gws);
+  gws = group_sum(gws);
   body_vel(ws, qaccws, lane); contact_base(ws, wi, ncon, jv, lane); simple_base(ws, wi, nsr, qaccws, SR_JV, lane);
-  __syncwarp();
+  gsync();
   body_vel(ws, qacc_smooth, lane); contact_base(ws, wi, ncon, ja, lane); simple_base(ws, wi, nsr, qacc_smooth, SR_JA, lane);
-  __syncwarp();
+  gsync();
   double cost_ws = gws + rows_cost(ws, wi, ncon, nsr, jv, SR_JV, lane), cost_0 = rows_cost(ws, wi, ncon, nsr, ja, SR_JA, lane);
   if (cost_ws < cost_0) {
     LANE_LOOP(d, nv) qacc[d] = qaccws[d];
     LANE_LOOP(i, ncon) { double* c = ws + L.con + i * L.cstride; for (int k = 0; k < wi[L.i_cdim + i]; k++) c[ja + k] = c[jv + k]; }
     LANE_LOOP(i, nsr) srv(ws, SR_JA, i) = srv(ws, SR_JV, i);
   }
-  __syncwarp();
+  gsync();
   mul_M(qM, Ma, qacc, lane);
   double cost_c = nt_update(ws, wi, ncon, nsr, lane), gauss = 0;
   LANE_LOOP(d, nv) gauss += 0.5 * (Ma[d] - qfrc_smooth[d]) * (qacc[d] - qacc_smooth[d]);
-  double cost = warp_sum(gauss) + cost_c;
+  double cost = group_sum(gauss) + cost_c;
   double scale = 1.0 / (m.meaninertia * (nv > 1 ? nv : 1));
   int niter = 0;
   for (int it = 0; it < m.iterations; it++) {
     double gn = 0;
     LANE_LOOP(d, nv) { double g = Ma[d] - qfrc_smooth[d] - qfc[d]; grad[d] = g; gn += g * g; }
-    gn = warp_sum(gn);
-    __syncwarp();
+    gn = group_sum(gn);
+    gsync();
     if (it > 0 && scale * sqrt(gn) < m.tolerance) break;
     if (it == 0) newton_barrier(sync);
     build_hessian(ws, wi, ncon, nsr, lane);
@@ -297,9 +294,9 @@ __device__ __noinline__ int solve_newton(double* ws, int* wi, int lane, int ncon
     mul_M(qM, Mv, search, lane);
     double g1 = 0, g2 = 0, sn = 0;
     LANE_LOOP(d, nv) { g1 += search[d] * (Ma[d] - qfrc_smooth[d]); g2 += 0.5 * search[d] * Mv[d]; sn += search[d] * search[d]; }
-    g1 = warp_sum(g1); g2 = warp_sum(g2); sn = sqrt(warp_sum(sn));
+    g1 = group_sum(g1); g2 = group_sum(g2); sn = sqrt(group_sum(sn));
     body_vel(ws, search, lane); contact_base(ws, wi, ncon, jv, lane); simple_base(ws, wi, nsr, search, SR_JV, lane);
-    __syncwarp();
+    gsync();
     if (it == 0) newton_barrier(sync);
     // exact line search: safeguarded 1-D Newton on the convex piecewise-quadratic cost along `search`
     double gtol = m.tolerance * 0.01 * sn * m.meaninertia * (nv > 1 ? nv : 1);
@@ -322,7 +319,7 @@ __device__ __noinline__ int solve_newton(double* ws, int* wi, int lane, int ncon
         double v = srv(ws, SR_JV, i), x = srv(ws, SR_JA, i) + alpha * v - srv(ws, SR_AREF, i);
         if (wi[L.i_srtype + i] == 0 || x < 0) { double D = srv(ws, SR_D, i); d1 += D * x * v; d2 += D * v * v; }
       }
-      d1 = warp_sum(d1) + g1 + 2 * g2 * alpha; d2 = warp_sum(d2) + 2 * g2;
+      d1 = group_sum(d1) + g1 + 2 * g2 * alpha; d2 = group_sum(d2) + 2 * g2;
       if (fabs(d1) < gtol) break;
       if (d1 < 0) lo = alpha; else hi = alpha;
       double next = alpha - d1 / d2;
@@ -335,12 +332,12 @@ __device__ __noinline__ int solve_newton(double* ws, int* wi, int lane, int ncon
     LANE_LOOP(d, nv) { qacc[d] += alpha * search[d]; Ma[d] += alpha * Mv[d]; }
     LANE_LOOP(i, ncon) { double* c = ws + L.con + i * L.cstride; for (int k = 0; k < wi[L.i_cdim + i]; k++) c[ja + k] += alpha * c[jv + k]; }
     LANE_LOOP(i, nsr) srv(ws, SR_JA, i) += alpha * srv(ws, SR_JV, i);
-    __syncwarp();
+    gsync();
     double oldcost = cost;
     cost_c = nt_update(ws, wi, ncon, nsr, lane);
     gauss = 0;
     LANE_LOOP(d, nv) gauss += 0.5 * (Ma[d] - qfrc_smooth[d]) * (qacc[d] - qacc_smooth[d]);
-    cost = warp_sum(gauss) + cost_c;
+    cost = group_sum(gauss) + cost_c;
     if (scale * (oldcost - cost) < m.tolerance) break;
   }
   return niter;

@@ -45,20 +45,20 @@ __device__ __noinline__ StepInfo forward(double* ws, int* wi, int lane, int* sta
   const double *qvel = ws + L.qvel, *ctrl = ws + L.ctl + CTL_CTRL;
   double *qfs = ws + L.qfrc_smooth, *qas = ws + L.qacc_smooth;
   LANE_LOOP(d, m.nv) qfs[d] = -m.dof_damping[d] * qvel[d] - qfs[d];
-  __syncwarp();
+  gsync();
   if (lane < m.nu) {
     double c = ctrl[lane], lo = m.actuator_ctrlrange[2 * lane], hi = m.actuator_ctrlrange[2 * lane + 1];
     c = c < lo ? lo : (c > hi ? hi : c);
     qfs[m.jnt_dofadr[m.actuator_jntid[lane]]] += m.actuator_gear[lane] * c;  // one actuator per joint in these scenes
   }
-  __syncwarp();
+  gsync();
   LANE_LOOP(d, m.nv) qas[d] = qfs[d];
-  __syncwarp();
+  gsync();
   // qacc_smooth = M^-1 qfrc_smooth: dense per-tree Cholesky in 8-lane groups (Hessian storage is free here); models with a
   // tree wider than a lane group fall back to the tree-sparse L^T D L factorisation
   if (!mass_block_solve(ws, qas, 0.0, lane)) {
     LANE_LOOP(i, m.nM) ws[L.qLD + i] = ws[L.qM + i];
-    __syncwarp();
+    gsync();
     factor_trees(ws + L.qLD, lane);
     solve_trees(ws + L.qLD, qas, lane);
   }
@@ -67,7 +67,7 @@ __device__ __noinline__ StepInfo forward(double* ws, int* wi, int lane, int* sta
   si.niter = solve_newton(ws, wi, lane, si.ncon, si.nsr, GE_STAGE_SYNC && sync);
   if (si.niter >= m.iterations) *status |= 4;
   LANE_LOOP(d, m.nv) ws[L.qaccws + d] = ws[L.qacc + d];
-  __syncwarp();
+  gsync();
   return si;
 }
 
@@ -79,20 +79,20 @@ __device__ __noinline__ StepInfo sim_step(double* ws, int* wi, int lane, int* st
   double h = m.timestep;
   double *acc = ws + L.grad, *qH = ws + L.qLD, *qvel = ws + L.qvel, *qpos = ws + L.qpos;
   LANE_LOOP(d, m.nv) acc[d] = ws[L.qfrc_smooth + d] + ws[L.qfrc_constraint + d];
-  __syncwarp();
+  gsync();
   if (!mass_block_solve(ws, acc, m.any_damping ? h : 0.0, lane)) {
     if (m.any_damping) {
       LANE_LOOP(i, m.nM) qH[i] = ws[L.qM + i];
-      __syncwarp();
+      gsync();
       LANE_LOOP(d, m.nv) qH[m.dof_Madr[d]] += h * m.dof_damping[d];
-      __syncwarp();
+      gsync();
       factor_trees(qH, lane);
     }
-    __syncwarp();
+    gsync();
     solve_trees(qH, acc, lane);
   }
   LANE_LOOP(d, m.nv) qvel[d] += h * acc[d];
-  __syncwarp();
+  gsync();
   bool bad = false;
   LANE_LOOP(j, m.njnt) {
     int qa = m.jnt_qposadr[j], d = m.jnt_dofadr[j], type = m.jnt_type[j];
@@ -105,8 +105,8 @@ __device__ __noinline__ StepInfo sim_step(double* ws, int* wi, int lane, int* st
     for (int k = 0; k < 4; k++) qpos[qa + k] = nq[k];
     if (!isfinite(nq[0])) bad = true;
   }
-  if (__any_sync(FULL, bad)) *status |= 2;
-  __syncwarp();
+  if (group_any(bad)) *status |= 2;
+  gsync();
   return si;
 }
 
@@ -123,8 +123,8 @@ __device__ __noinline__ double pid_and_delta(double* ws, int lane, int group_mas
     ctl[CTL_LAST + lane] = x; ctl[CTL_CTRL + lane] = u;
     if (group_mask >> lane & 1) delta = fabs(ctl[CTL_TARGET + lane] - x);
   }
-  delta = warp_max(delta);
-  __syncwarp();
+  delta = group_max(delta);
+  gsync();
   return delta;
 }
 
@@ -172,7 +172,7 @@ enum { PH_NONE = 0, PH_PRE = 1, PH_PRE_CENTRE = 2, PH_ROTATE = 3, PH_OPEN_HALF =
 __device__ __noinline__ void start_group(Cmd& c, double* ws, int lane, int mask, const double* target, double tol, int maxsteps) {
   const Layout& L = c_L;
   if (target && lane == 0) { int k = 0; for (int i = 0; i < GE_NU; i++) if (mask >> i & 1) ws[L.ctl + CTL_TARGET + i] = target[k++]; }
-  __syncwarp();
+  gsync();
   c.active = 1; c.mask = mask; c.tol = tol; c.maxsteps = maxsteps; c.steps = 1; c.result = 0; c.reached = 0;
 }
 __device__ __noinline__ void start_ee(Cmd& c, double* ws, int lane, const double* xyz, const double* base, double tol, int maxsteps) {
@@ -243,7 +243,7 @@ __device__ __noinline__ bool prog_advance(Prog& p, Cmd& c, double* ws, int lane,
         p.grasp = c.result != 1; info[5] = c.steps;
       to_centre:
         if (lane == 0) ws[L.ctl + CTL_KP + 0] = 10.0;  // GraspingEnv.py:282
-        __syncwarp();
+        gsync();
         p.phase = PH_CENTRE;
         start_ee(c, ws, lane, centre, base, 0.05, 1000);
         if (c.active) return true;
@@ -292,7 +292,7 @@ __device__ __noinline__ bool prog_advance(Prog& p, Cmd& c, double* ws, int lane,
       case PH_ROTATE_BACK:
         info[10] = c.steps; info[11] = p.grasp;
         if (lane == 0) ws[L.ctl + CTL_KP + 0] = 20.0;  // GraspingEnv.py:347
-        __syncwarp();
+        gsync();
         p.phase = PH_NONE;
         return false;
       case PH_STAY_ONLY:

@@ -13,11 +13,17 @@
 #define ge ge_smem
 #define GE_API(n) n##_smem
 #define GE_WS_IN_HBM 0
+#define GE_LANES 32   // threads that cooperate on one environment: one warp
 #else
 #define ge ge_hbm
 #define GE_API(n) n##_hbm
 #define GE_WS_IN_HBM 1
+// r02: the big-scene variant gives every environment a whole CTA of 4 warps.  The stage code is the same source: lane loops stride
+// by GE_LANES, `gsync()` is __syncthreads(), reductions go through shared memory, and the pieces that are inherently warp-shaped
+// (MPR on one geom pair, the 8-lane tree groups, one dense island factorisation) are dealt out to the 4 warps.
+#define GE_LANES 128
 #endif
+#define GE_NW (GE_LANES / 32)
 #define GE_ERR_TOO_LARGE (-100)  // internal: variant 0 cannot hold the scene, the dispatcher then creates variant 1
 
 #define ge_last_error GE_API(ge_last_error)

@@ -55,14 +55,14 @@ __device__ __forceinline__ void env_load(const EnvArrays& E, int env, double* ws
   r.reward = __ldcg(E.reward + env); r.status = __ldcg(E.status + env); r.nstep = 0;
   LANE_LOOP(i, m.nq) ws[L.qpos + i] = __ldcg(E.qpos + (size_t)env * m.nq + i);
   LANE_LOOP(i, m.nv) { ws[L.qvel + i] = __ldcg(E.qvel + (size_t)env * m.nv + i); ws[L.qaccws + i] = __ldcg(E.qaccws + (size_t)env * m.nv + i); }
-  ws[L.ctl + lane] = __ldcg(E.ctl + (size_t)env * 32 + lane);
-  __syncwarp();
+  if (lane < 32) ws[L.ctl + lane] = __ldcg(E.ctl + (size_t)env * 32 + lane);
+  gsync();
 }
 __device__ __forceinline__ void env_store(const EnvArrays& E, int env, const double* ws, int lane, const EnvRegs& r) {
   const DevModel& m = c_m; const Layout& L = c_L;
   LANE_LOOP(i, m.nq) E.qpos[(size_t)env * m.nq + i] = ws[L.qpos + i];
   LANE_LOOP(i, m.nv) { E.qvel[(size_t)env * m.nv + i] = ws[L.qvel + i]; E.qaccws[(size_t)env * m.nv + i] = ws[L.qaccws + i]; }
-  E.ctl[(size_t)env * 32 + lane] = ws[L.ctl + lane];
+  if (lane < 32) E.ctl[(size_t)env * 32 + lane] = ws[L.ctl + lane];
   if (lane == 0) {
     E.cmd_active[env] = r.c.active; E.cmd_mask[env] = r.c.mask; E.cmd_maxsteps[env] = r.c.maxsteps; E.cmd_steps[env] = r.c.steps;
     E.cmd_result[env] = r.c.result; E.cmd_tol[env] = r.c.tol;
@@ -73,6 +73,20 @@ __device__ __forceinline__ void env_store(const EnvArrays& E, int env, const dou
   }
 }
 
+__device__ __forceinline__ unsigned long long group_bcast_u64(unsigned long long v, int lane) {
+#if GE_NW == 1
+  return __shfl_sync(FULL, v, 0);
+#else
+  __shared__ unsigned long long b;
+  if (lane == 0) b = v;
+  __syncthreads();
+  unsigned long long r = b;
+  __syncthreads();
+  return r;
+#endif
+}
+// blockDim = (GE_LANES, envs per CTA): threadIdx.x is the lane inside the group that owns one environment (a warp; a whole CTA of
+// GE_NW warps in the big-scene build, where blockDim.y = 1)
 __global__ void __launch_bounds__(256) k_run(EnvArrays E, int n_env, int nsub, int quota, unsigned long long ticket_base, double base_x, double base_y,
                                              double base_z, int stage_sync) {
   extern __shared__ double smem[];
@@ -91,20 +105,20 @@ __global__ void __launch_bounds__(256) k_run(EnvArrays E, int n_env, int nsub, i
   int env = -1, left = 0;
   bool exhausted = false, running = false;
   for (;;) {
-    // ---- a warp without an environment takes tasks until it finds a busy, unlocked environment (or the launch has none left)
+    // ---- a group without an environment takes tasks until it finds a busy, unlocked environment (or the launch has none left)
     while (env < 0 && !exhausted) {
       unsigned long long t = 0;
       if (lane == 0) t = atomicAdd(E.ticket, 1ULL) - ticket_base;
-      t = __shfl_sync(FULL, t, 0);
+      t = group_bcast_u64(t, lane);
       if (t >= total) { exhausted = true; break; }
       const int e = (int)(t % (unsigned long long)n_env), v = (int)(t / (unsigned long long)n_env);
       if (!env_is_busy(E, e)) continue;
       int got = 0;
       if (lane == 0) got = atomicCAS(E.lock + e, 0, 1) == 0;
-      got = __shfl_sync(FULL, got, 0);
-      if (!got) continue;  // an earlier visit of this env is still running on another warp: this visit is dropped, never waited for
+      got = group_bcast_int(got, lane);
+      if (!got) continue;  // an earlier visit of this env is still running elsewhere: this visit is dropped, never waited for
       __threadfence();
-      if (!env_is_busy(E, e)) { __syncwarp(); if (lane == 0) atomicExch(E.lock + e, 0); continue; }
+      if (!env_is_busy(E, e)) { gsync(); if (lane == 0) atomicExch(E.lock + e, 0); continue; }
 #if GE_WS_IN_HBM
       ws = E.gws + (size_t)e * (L.total_bytes / 8);
 #endif
@@ -135,9 +149,10 @@ __global__ void __launch_bounds__(256) k_run(EnvArrays E, int n_env, int nsub, i
     if (--left <= 0 || !running) {
       // a movement that just ended inside the last iteration still has to hand over to the program (no sub-step involved)
       while (!r.c.active && r.p.phase != PH_NONE) { if (!prog_advance(r.p, r.c, ws, lane, base, r.info, &r.reward)) break; }
+      gsync();
       env_store(E, env, ws, lane, r);
       __threadfence();
-      __syncwarp();
+      gsync();
       if (lane == 0) atomicExch(E.lock + env, 0);
       env = -1;
     }
@@ -152,7 +167,7 @@ __global__ void k_count_busy(EnvArrays E, int n_env) {
 }
 
 // forward pipeline on one env, selected intermediate copied out (parity tests); no integration
-__global__ void __launch_bounds__(32) k_debug(EnvArrays E, int env, int field, double* out, int cap, int* nout) {
+__global__ void __launch_bounds__(GE_LANES) k_debug(EnvArrays E, int env, int field, double* out, int cap, int* nout) {
   extern __shared__ double smem[];
   const DevModel& m = c_m; const Layout& L = c_L;
   int lane = threadIdx.x;
@@ -164,8 +179,8 @@ __global__ void __launch_bounds__(32) k_debug(EnvArrays E, int env, int field, d
   int* wi = (int*)(ws + L.total_doubles);
   LANE_LOOP(i, m.nq) ws[L.qpos + i] = E.qpos[(size_t)env * m.nq + i];
   LANE_LOOP(i, m.nv) { ws[L.qvel + i] = E.qvel[(size_t)env * m.nv + i]; ws[L.qaccws + i] = E.qaccws[(size_t)env * m.nv + i]; }
-  ws[L.ctl + lane] = E.ctl[(size_t)env * 32 + lane];
-  __syncwarp();
+  if (lane < 32) ws[L.ctl + lane] = E.ctl[(size_t)env * 32 + lane];
+  gsync();
   int status = 0, n = 0;
   if (field <= 2) {  // kinematics only: 0 xpos, 1 xmat, 2 cdof
     stage_fk(ws, lane);
@@ -175,7 +190,7 @@ __global__ void __launch_bounds__(32) k_debug(EnvArrays E, int env, int field, d
   } else if (field == 3 || field == 4) {  // 3 qM (sparse), 4 qfrc_bias
     stage_fk(ws, lane); stage_rne(ws, lane);
     if (field == 4) { n = m.nv; LANE_LOOP(i, (n < cap ? n : cap)) out[i] = ws[L.qfrc_smooth + i]; }
-    else { __syncwarp(); stage_crb(ws, lane); n = m.nM; LANE_LOOP(i, (n < cap ? n : cap)) out[i] = ws[L.qM + i]; }
+    else { gsync(); stage_crb(ws, lane); n = m.nM; LANE_LOOP(i, (n < cap ? n : cap)) out[i] = ws[L.qM + i]; }
   } else {
     StepInfo si = forward(ws, wi, lane, &status);
     if (field == 5 || field == 6 || field == 7) {
@@ -266,7 +281,7 @@ __global__ void k_ctrl(EnvArrays E, int n_env, const double* in, double* out, co
 }
 // `nsub` bare sim.step() calls with the controls as they stand (no PID evaluation): what a caller of the reference gets from
 // sim.step() after actuate_joint_group (MujocoController.py:256-267, :611).  One warp per CTA; not a throughput path.
-__global__ void __launch_bounds__(32) k_step_open(EnvArrays E, int n_env, int nsub, const unsigned char* emask) {
+__global__ void __launch_bounds__(GE_LANES) k_step_open(EnvArrays E, int n_env, int nsub, const unsigned char* emask) {
   extern __shared__ double smem[];
   const DevModel& m = c_m; const Layout& L = c_L;
   int env = blockIdx.x, lane = threadIdx.x;
@@ -279,8 +294,8 @@ __global__ void __launch_bounds__(32) k_step_open(EnvArrays E, int n_env, int ns
   int* wi = (int*)(ws + L.total_doubles);
   LANE_LOOP(i, m.nq) ws[L.qpos + i] = E.qpos[(size_t)env * m.nq + i];
   LANE_LOOP(i, m.nv) { ws[L.qvel + i] = E.qvel[(size_t)env * m.nv + i]; ws[L.qaccws + i] = E.qaccws[(size_t)env * m.nv + i]; }
-  ws[L.ctl + lane] = E.ctl[(size_t)env * 32 + lane];
-  __syncwarp();
+  if (lane < 32) ws[L.ctl + lane] = E.ctl[(size_t)env * 32 + lane];
+  gsync();
   int status = E.status[env];
   for (int it = 0; it < nsub; it++) sim_step(ws, wi, lane, &status, false);
   LANE_LOOP(i, m.nq) E.qpos[(size_t)env * m.nq + i] = ws[L.qpos + i];
@@ -311,14 +326,14 @@ __global__ void k_pixel_2_world(int n, int cam, int W, int H, const int* px, con
   v3add(t, pc, m.cam_pos0 + 3 * cam);
   m3Tmulv(xyz + 3 * i, m.cam_mat0 + 9 * cam, t);  // inverse of a rotation matrix = transpose
 }
-__global__ void __launch_bounds__(32) k_body_xpos(EnvArrays E, int n_env, double* xpos) {
+__global__ void __launch_bounds__(GE_LANES) k_body_xpos(EnvArrays E, int n_env, double* xpos) {
   extern __shared__ double smem[];
   const DevModel& m = c_m; const Layout& L = c_L;
   int env = blockIdx.x, lane = threadIdx.x;
   if (env >= n_env) return;
   double* ws = smem;
   LANE_LOOP(i, m.nq) ws[L.qpos + i] = E.qpos[(size_t)env * m.nq + i];
-  __syncwarp();
+  gsync();
   stage_fk(ws, lane);
   LANE_LOOP(i, 3 * m.nbody) xpos[(size_t)env * 3 * m.nbody + i] = ws[L.xpos + i];
 }
@@ -504,7 +519,8 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
   CK(cudaMemcpyToSymbol(c_L, &h->lay, sizeof(Layout)));
   // warps (= envs) per CTA: maximise the resident warps per SM (228 KB shared memory per SM, 1 KB reserved per CTA, 227 KB max per
   // CTA); ties go to the smaller CTA (less barrier imbalance).  r01 sweeps are in DESIGN.md; GE_WPB overrides.
-  if (h->lay.ws_global) h->wpb = 4;
+  if (GE_NW > 1) h->wpb = 1;  // CTA-per-env build: one environment per CTA of GE_NW warps
+  else if (h->lay.ws_global) h->wpb = 4;
   else {
     int best = 1, best_warps = 0;
     for (int w = 1; w <= 8; w++) {
@@ -518,7 +534,8 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
   }
   h->stage_sync = h->lay.ws_global ? 0 : 1;  // lock-step CTAs pay off for the small scene only (equal work per env, code-fetch bound)
   if (const char* ev = getenv("GE_STAGE_SYNC")) h->stage_sync = atoi(ev) != 0;
-  if (const char* ev = getenv("GE_WPB")) { int v = atoi(ev); if (v >= 1 && v <= 8 && (h->lay.ws_global || v * h->lay.total_bytes <= 227 * 1024)) h->wpb = v; }
+  if (GE_NW > 1) h->stage_sync = 0;
+  if (const char* ev = getenv("GE_WPB")) if (GE_NW == 1) { int v = atoi(ev); if (v >= 1 && v <= 8 && (h->lay.ws_global || v * h->lay.total_bytes <= 227 * 1024)) h->wpb = v; }
   h->ws_smem = h->lay.ws_global ? 0 : (size_t)h->lay.total_bytes;
   if (h->ws_smem) {
     CK(cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, h->wpb * h->lay.total_bytes));
@@ -537,11 +554,11 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
   AL(E.prog_coords, double, N * 3); AL(E.prog_table, double, N); AL(E.reward, unsigned char, N); AL(E.status, int, N); AL(E.substeps, long long, N);
   AL(E.busy_count, int, 1); AL(E.lock, int, N); AL(E.ticket, unsigned long long, 1);
   h->ticket_base = 0;
-  h->quota = 64;
+  h->quota = 32;  // r02c sweep at 4096 envs: 32 -> 3.89 M, 64 -> 3.81 M, 128 -> 3.59 M, 256 (= one visit per launch) -> 3.24 M sub-steps/s
   if (const char* ev = getenv("GE_QUOTA")) { int v = atoi(ev); if (v >= 1) h->quota = v; }
   {
     int per_sm = 0, sms = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_run, 32 * h->wpb, (size_t)h->wpb * h->ws_smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_run, GE_LANES * h->wpb, (size_t)h->wpb * h->ws_smem));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     h->max_ctas = per_sm * sms > 0 ? per_sm * sms : 1;
   }
@@ -625,7 +642,7 @@ extern "C" int ge_get_state(ge_handle h, double* qpos, double* qvel) {
 extern "C" int ge_get_body_xpos(ge_handle h, double* xpos) {
   if (!h || !xpos) return GE_ERR_ARG;
   if (bind(h)) return GE_ERR_CUDA;
-  k_body_xpos<<<h->n_envs, 32, h->lay.fk_bytes, h->stream>>>(h->E, h->n_envs, xpos);
+  k_body_xpos<<<h->n_envs, GE_LANES, h->lay.fk_bytes, h->stream>>>(h->E, h->n_envs, xpos);
   h->launches++;
   CK(cudaGetLastError());
   return GE_OK;
@@ -667,14 +684,14 @@ extern "C" int ge_grasp(ge_handle h, const double* coords, const int32_t* rot, d
 extern "C" int ge_run_async(ge_handle h, int substeps) {
   if (!h || substeps <= 0) return fail(GE_ERR_ARG, "ge_run_async: bad argument");
   if (bind(h)) return GE_ERR_CUDA;
-  dim3 blk(32, h->wpb);
+  dim3 blk(GE_LANES, h->wpb);
   int ctas = (h->n_envs + h->wpb - 1) / h->wpb;
   if (ctas > h->max_ctas) ctas = h->max_ctas;  // persistent grid: environments are handed to warps dynamically
   int quota = h->quota < substeps ? h->quota : substeps;
   k_run<<<ctas, blk, (size_t)h->wpb * h->ws_smem, h->stream>>>(h->E, h->n_envs, substeps, quota, h->ticket_base, h->base_pos[0], h->base_pos[1],
                                                                 h->base_pos[2], h->stage_sync);
   // every warp takes tasks until it has drawn one beyond the launch's range: n_env * visits real tasks + one overshoot per warp
-  h->ticket_base += (unsigned long long)h->n_envs * ((substeps + quota - 1) / quota) + (unsigned long long)ctas * h->wpb;
+  h->ticket_base += (unsigned long long)h->n_envs * ((substeps + quota - 1) / quota) + (unsigned long long)ctas * h->wpb;  // (one drawing group per env slot)
   h->launches++; h->substep_launches++;
   CK(cudaGetLastError());
   return GE_OK;
@@ -757,7 +774,7 @@ extern "C" int ge_get_ctrl(ge_handle h, double* ctrl) {
 extern "C" int ge_step_open_loop(ge_handle h, int substeps, const uint8_t* env_mask) {
   if (!h || substeps <= 0) return fail(GE_ERR_ARG, "ge_step_open_loop: bad argument");
   if (bind(h)) return GE_ERR_CUDA;
-  k_step_open<<<h->n_envs, 32, h->ws_smem, h->stream>>>(h->E, h->n_envs, substeps, env_mask);
+  k_step_open<<<h->n_envs, GE_LANES, h->ws_smem, h->stream>>>(h->E, h->n_envs, substeps, env_mask);
   h->launches++; h->substep_launches++;
   CK(cudaGetLastError());
   return GE_OK;
@@ -802,7 +819,7 @@ extern "C" int ge_debug_forward(ge_handle h, int env, const char* field, double*
   for (int i = 0; i < 12; i++) if (!strcmp(names[i], field)) f = i;
   if (f < 0) return fail(GE_ERR_ARG, "ge_debug_forward: unknown field %s", field);
   if (cap > (1 << 16)) cap = 1 << 16;
-  k_debug<<<1, 32, h->ws_smem, h->stream>>>(h->E, env, f, h->d_dbg, cap, h->d_nout);
+  k_debug<<<1, GE_LANES, h->ws_smem, h->stream>>>(h->E, env, f, h->d_dbg, cap, h->d_nout);
   h->launches++;
   CK(cudaGetLastError());
   int n = 0;

@@ -139,7 +139,9 @@ def test_batched_env_scene_b_reset_and_step():
 
 
 def test_hbm_workspace_path_matches_shared_memory_path(scene_a):
-    """the same scene-A trajectory with the workspace in shared memory and (GE_WS_GLOBAL=1) in HBM rows: bit-identical"""
+    """the same scene-A trajectory through both builds of the engine: warp-per-env with the workspace in shared memory, and
+    (GE_WS_GLOBAL=1) the big-scene build, a CTA of 4 warps per env.  Same arithmetic per item; the reductions over dofs / contacts
+    are summed in a different (each fixed) order, so the two agree to rounding, not bit for bit."""
     from mujoco_rl_ur5_b200.engine import BatchedEngine
 
     blob, A, _ = scene_a
@@ -159,7 +161,7 @@ def test_hbm_workspace_path_matches_shared_memory_path(scene_a):
         q, v = eng.get_state()
         res.append((q.cpu().numpy().copy(), v.cpu().numpy().copy()))
         eng.close()
-    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert np.abs(res[0][0] - res[1][0]).max() < 1e-9 and np.abs(res[0][1] - res[1][1]).max() < 1e-7
 
 
 def test_facade_opens_reference_default_scene():
