@@ -144,124 +144,9 @@ __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Warp-specialised main loop, 160 threads: warps 0-3 are producers (cp.async gathers into a ring of STAGES shared-memory stages,
-// each thread signalling the stage's "full" mbarrier when its copies have landed), one thread of warp 4 waits for "full", issues the
-// tcgen05.mma group of the k-step and commits it onto the stage's "empty" mbarrier.  No CTA-wide barrier inside the loop.
-// (first version, kept selectable with GQ_KERNEL=1 for A/B runs: ~700 producer instructions per warp and k-step, profiles/r01h)
-template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(160) k_conv_tc_v1(const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ bias,
-                                                 float* __restrict__ y, float* __restrict__ stats, int H, int W, int Cin, int Cout, int ks) {
-  constexpr int A_STAGE = BM * BK * 2, B_STAGE = BLOCK_N * BK * 2;  // bytes
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_STAGE;
-  uint64_t* full = (uint64_t*)(smem + STAGES * (A_STAGE + B_STAGE));  // [STAGES] copies landed (128 producer arrivals)
-  uint64_t* empty = full + STAGES;                                    // [STAGES] MMAs that read the stage are done (1 commit)
-  uint64_t* accbar = empty + STAGES;                                  // accumulator complete
-  uint32_t* tmem_slot = (uint32_t*)(accbar + 1);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int HW = H * W, m0 = blockIdx.x * BM, n0 = blockIdx.y * BLOCK_N, b = blockIdx.z;
-  const int pad = ks / 2, taps = ks * ks, kchunks = Cin / BK, nk = taps * kchunks;
-  if (tid == 0) {
-    for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
-    mbar_init(accbar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, BLOCK_N);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tacc = *tmem_slot;
-  constexpr uint32_t idesc = make_idesc(BM, BLOCK_N);
-  // copy mapping: consecutive lanes take consecutive 16-byte chunks of the same row (pixel / output channel), so a warp-level
-  // cp.async reads 4 full 128-byte lines and writes 4 swizzled 128-byte smem rows (conflict-free); thread -> chunk tid % 8 of
-  // rows tid / 8 + 16 * i
-  const int chunk = tid & 7, rbase = tid >> 3;
-  const bf16* xb = x + (size_t)b * HW * Cin;
-  int pix[8];  // (oh << 16) | ow of this thread's 8 A rows, -1 past the image
-#pragma unroll
-  for (int i = 0; i < 8; i++) { const int mm = m0 + rbase + 16 * i; pix[i] = mm < HW ? ((mm / W) << 16) | (mm % W) : -1; }
-  auto issue_loads = [&](int kn) {
-    const int sn = kn % STAGES, tap = kn / kchunks, c0 = (kn % kchunks) * BK;
-    const int dh = tap / ks - pad, dw = tap % ks - pad;
-    uint8_t* dstA = sA + sn * A_STAGE;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const int row = rbase + 16 * i, ih = (pix[i] >> 16) + dh, iw = (pix[i] & 0xffff) + dw;
-      const bool ok = pix[i] >= 0 && ih >= 0 && ih < H && iw >= 0 && iw < W;
-      const bf16* src = ok ? xb + ((size_t)ih * W + iw) * Cin + c0 + chunk * 8 : xb;
-      cp_async16(dstA + row * 128 + ((chunk ^ (row & 7)) << 4), src, ok ? 16u : 0u);
-    }
-    uint8_t* dstB = sB + sn * B_STAGE;
-#pragma unroll
-    for (int i = 0; i < BLOCK_N / 16; i++) {
-      const int row = rbase + 16 * i;
-      cp_async16(dstB + row * 128 + ((chunk ^ (row & 7)) << 4), w + ((size_t)(n0 + row) * taps + tap) * Cin + c0 + chunk * 8, 16u);
-    }
-  };
-  if (warp < 4) {
-    for (int kn = 0; kn < nk; kn++) {
-      const int sn = kn % STAGES;
-      if (kn >= STAGES) mbar_wait(&empty[sn], ((kn - STAGES) / STAGES) & 1);  // the MMAs of k-step kn - STAGES have read the stage
-      issue_loads(kn);
-      cp_async_mbar_arrive(&full[sn]);
-    }
-  } else if (lane == 0) {
-    for (int kb = 0; kb < nk; kb++) {
-      const int s = kb % STAGES;
-      mbar_wait(&full[s], (kb / STAGES) & 1);
-      fence_proxy_async();  // generic-proxy (cp.async) smem writes -> visible to the tensor core (async proxy)
-      tc_fence_after();
-      const uint32_t a_base = smem_u32(sA + s * A_STAGE), b_base = smem_u32(sB + s * B_STAGE);
-#pragma unroll
-      for (int k = 0; k < BK / 16; k++) {  // UMMA_K = 16 bf16 = 32 bytes inside the swizzle atom
-        uint64_t adesc = make_smem_desc_sw128(a_base + k * 32);
-        uint64_t bdesc = make_smem_desc_sw128(b_base + k * 32);
-        umma_bf16(tacc, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-      }
-      umma_commit(&empty[s]);
-      if (kb == nk - 1) umma_commit(accbar);
-    }
-  }
-  if (warp < 4) {
-  mbar_wait(accbar, 0);
-  tc_fence_after();
-  // ---- epilogue: TMEM -> registers -> global fp32 (+bias), per-channel batch-norm statistics
-  const int m = m0 + tid;  // epilogue: thread t of warp w holds accumulator row 32 w + t
-  const bool mvalid = m < HW;
-  float* yrow = y + ((size_t)b * HW + m) * Cout + n0;
-  for (int cb = 0; cb < BLOCK_N; cb += 32) {
-    float v[32];
-    tmem_ld32(tacc + ((uint32_t)(warp * 32) << 16) + cb, v);
-    if (bias) {
-#pragma unroll
-      for (int i = 0; i < 32; i++) v[i] += bias[n0 + cb + i];
-    }
-    if (mvalid) {
-      float4* dst = (float4*)(yrow + cb);
-#pragma unroll
-      for (int i = 0; i < 8; i++) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    }
-    if (stats) {
-#pragma unroll
-      for (int i = 0; i < 32; i++) {
-        float s1 = mvalid ? v[i] : 0.f, s2 = s1 * s1;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-        // deterministic: every (CTA, warp) writes its own partial, k_bn_reduce adds them in a fixed order
-        if (lane == 0) { float* pp = stats + ((((size_t)b * gridDim.x + blockIdx.x) * 4 + warp) * Cout + n0 + cb + i) * 2; pp[0] = s1; pp[1] = s2; }
-      }
-    }
-  }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tacc, BLOCK_N);
-}
-
-
-// ---- second version of the convolution kernel (default).  Same tiling, shared-memory layout, barrier protocol and MMA issue as v1;
-// what changed is what the ncu capture of v1 showed to be the limit (profiles/r01h_conv_tc_ncu_summary.txt: tensor pipe 17-23 % active,
+// ---- non-persistent convolution kernel (GQ_PERSIST=0; the default until r02a, kept as the A/B partner of the persistent TMA kernel
+// below and as the path for drivers without cuTensorMapEncodeIm2col).  Same tiling, shared-memory layout, barrier protocol and MMA
+// issue as the first version of round 1 (removed in r02); what changed is what the ncu capture of v1 showed to be the limit (profiles/r01h_conv_tc_ncu_summary.txt: tensor pipe 17-23 % active,
 // issue slots 30-44 % busy with 1.25 resident warps per scheduler = the four producer warps executing ~700 instructions per k-step):
 //  * producer address arithmetic is hoisted out of the k-loop: every thread's 8 A rows and BLOCK_N/16 B rows are an arithmetic
 //    progression in global memory (row stride 16 pixels / 16 output channels) and in shared memory (2048 B: 16 rows x 128 B, the
@@ -419,7 +304,7 @@ __global__ void __launch_bounds__(32 * (NPW + 1)) k_conv_tc(const __grid_constan
   if (warp == 0) tmem_dealloc(tacc, BLOCK_N);
 }
 // epilogue of one 128 x BLOCK_N accumulator (TMEM columns tcol .. tcol + BLOCK_N - 1) for the warp owning lane quarter `quarter`:
-// the same arithmetic as the epilogue of k_conv_tc (shared by the two experimental persistent kernels)
+// the same arithmetic as the epilogue of k_conv_tc
 template <int BLOCK_N, int EPI>
 __device__ __forceinline__ void conv_epilogue_tile(uint32_t tcol, int quarter, int lane, int mt, int n0, int b, int gx, int HW, int Cout,
                                                    const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ stats,
@@ -470,115 +355,10 @@ __device__ __forceinline__ void conv_epilogue_tile(uint32_t tcol, int quarter, i
   }
 }
 
-// ---- EXPERIMENTAL (GQ_PERSIST=1, default off; written after the GPU budget of round 1 was spent: compiled, never run — the first thing
-// to test in round 2).  Persistent form of k_conv_tc: one CTA per SM walks a static round-robin list of (m tile, n tile, image) tiles,
-// the accumulator is double-buffered in TMEM (2 x BLOCK_N columns) and the epilogue has its own 4 warps, so the TMEM read-out, the stores
-// and the BatchNorm partial sums of tile i overlap the main loop of tile i + 1, and the per-tile costs of a CTA (launch, TMEM allocation,
-// barrier initialisation) are paid once.  Roles: warps 0-7 producers (cp.async activation gather, thread 0 also issues the weight TMA),
-// warp 8 lane 0 issues the MMAs, warps 9-12 are the epilogue (lane quarter = warp % 4).  The smem ring, its full / empty barriers and the
-// gather plan are those of k_conv_tc, with the stage / phase counters running across tiles; acc_full[a] (1 commit) / acc_empty[a]
-// (128 epilogue arrivals) hand the accumulator buffers back and forth.
-template <int BLOCK_N, int STAGES, int EPI>
-__global__ void __launch_bounds__(416) k_conv_tc_persist(const __grid_constant__ CUtensorMap tmap_w, const bf16* __restrict__ x, const float* __restrict__ bias,
-                                                         float* __restrict__ y, float* __restrict__ stats, const float* __restrict__ resid,
-                                                         const float2* __restrict__ scale_shift, bf16* __restrict__ out, int H, int W, int Cin, int Cout,
-                                                         int ks, int gx, int gy, int ntiles) {
-  constexpr int A_STAGE = BM * BK * 2, B_STAGE = BLOCK_N * BK * 2, NPW = 8, RS = 4 * NPW;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_STAGE;
-  uint64_t* full = (uint64_t*)(smem + STAGES * (A_STAGE + B_STAGE));
-  uint64_t* empty = full + STAGES;
-  uint64_t* acc_full = empty + STAGES;   // [2]
-  uint64_t* acc_empty = acc_full + 2;    // [2]
-  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int HW = H * W, pad = ks / 2, taps = ks * ks, kchunks = Cin / BK, nk = taps * kchunks;
-  if (tid == 0) {
-    for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 32 * NPW + 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, 2 * BLOCK_N);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tacc = *tmem_slot;
-  constexpr uint32_t idesc = make_idesc(BM, BLOCK_N);
-  if (warp < NPW) {
-    // ---- producers
-    int sn = 0, round = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      const int mt = t % gx, nt = (t / gx) % gy, b = t / (gx * gy);
-      const int m0 = mt * BM, n0 = nt * BLOCK_N;
-      ConvPlan p;
-      conv_plan_init<RS>(p, tid, m0, n0, H, W, Cin, ks);
-      p.sn = sn; p.round = round;  // the ring keeps turning across tiles
-      const uint32_t sA_u = smem_u32(sA) + p.dstoff;
-      const char* xb = (const char*)(x + (size_t)b * HW * Cin);
-      for (int kn = 0; kn < nk; kn++) {
-        if (p.round > 0) mbar_wait(&empty[p.sn], (uint32_t)(p.round - 1) & 1u);
-        const uint32_t tbit = 1u << p.tap;
-        const char* ap = xb + conv_plan_a(p, W, Cin);
-        const uint32_t da = sA_u + (uint32_t)(p.sn * A_STAGE);
-#pragma unroll
-        for (int i = 0; i < BM / RS; i++) {
-          const bool ok = (p.vmask[i] & tbit) != 0;
-          cp_async16_s(da + i * (RS * 128), ok ? (const void*)ap : (const void*)xb, ok ? 16u : 0u);
-          ap += p.a_stride;
-        }
-        if (tid == 0) {
-          mbar_arrive_expect_tx(&full[p.sn], (uint32_t)B_STAGE);
-          tma_load_2d(smem_u32(sB) + (uint32_t)(p.sn * B_STAGE), &tmap_w, kn * BK, n0, &full[p.sn]);
-        }
-        cp_async_mbar_arrive(&full[p.sn]);
-        conv_plan_next(p, STAGES, kchunks, pad);
-      }
-      sn = p.sn; round = p.round;
-    }
-  } else if (warp == NPW) {
-    // ---- MMA issuer
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0; int i = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
-        const int a = i & 1;
-        mbar_wait(&acc_empty[a], (uint32_t)((i >> 1) & 1) ^ 1u);  // buffer drained by the epilogue of tile i - 2 (passes at once for i < 2)
-        tc_fence_after();
-        const uint32_t dacc = tacc + (uint32_t)(a * BLOCK_N);
-        for (int kb = 0; kb < nk; kb++) {
-          mbar_wait(&full[s], ph);
-          fence_proxy_async();
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + s * A_STAGE), b_base = smem_u32(sB + s * B_STAGE);
-#pragma unroll
-          for (int k = 0; k < BK / 16; k++)
-            umma_bf16(dacc, make_smem_desc_sw128(a_base + k * 32), make_smem_desc_sw128(b_base + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty[s]);
-          if (kb == nk - 1) umma_commit(&acc_full[a]);
-          if (++s == STAGES) { s = 0; ph ^= 1u; }
-        }
-      }
-    }
-  } else {
-    // ---- epilogue warps 9..12: lane quarter warp % 4
-    const int quarter = warp & 3;
-    int i = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
-      const int mt = t % gx, nt = (t / gx) % gy, b = t / (gx * gy);
-      const int a = i & 1;
-      mbar_wait(&acc_full[a], (uint32_t)(i >> 1) & 1u);
-      tc_fence_after();
-      conv_epilogue_tile<BLOCK_N, EPI>(tacc + (uint32_t)(a * BLOCK_N), quarter, lane, mt, nt * BLOCK_N, b, gx, HW, Cout, bias, y, stats, resid, scale_shift, out);
-      tc_fence_before();  // the tcgen05.ld of this buffer are complete (wait::ld inside tmem_ld32): hand it back to the MMA warp
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[a])) : "memory");
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tacc, 2 * BLOCK_N);
-}
-
-// ---- EXPERIMENTAL (GQ_PERSIST=2, default off, compiled but never run in round 1): the persistent kernel fed by TMA only.  The
+// ---- DEFAULT since r02a: the persistent kernel fed by TMA only (whole forward 477 vs 439 TFLOP/s, profiles/r02a_qnet_sweep.txt; a
+// second persistent variant with a cp.async activation gather measured 409 and was deleted).  One CTA per SM walks a static
+// round-robin list of (m tile, n tile, image) tiles; the accumulator is double-buffered in TMEM (2 x BLOCK_N columns) and the epilogue
+// has its own 4 warps, so the TMEM read-out, the stores and the BatchNorm partials of tile i overlap the main loop of tile i + 1.  The
 // activation operand is an **im2col-mode** tensor map over x [N][H][W][C] (cuTensorMapEncodeIm2col: pixel box corners (-pad, -pad) /
 // (pad - (ks - 1), ...), 64 channels per pixel, 128 pixels per column, 128-byte swizzle): one
 // `cp.async.bulk.tensor.4d...im2col` per k-step loads the 128 consecutive output positions of the tile for filter tap (offset_w, offset_h)
@@ -970,30 +750,24 @@ extern "C" int gq_obs_to_state(const unsigned char* rgb, const float* depth, flo
   QCK(cudaGetLastError());
   return 0;
 }
-extern "C" const char* gq_version(void) { return "grasp_qnet 0.4 sm_100a bf16 tcgen05 (warp-specialised producers: cp.async activation gather + TMA weight tiles, SW128 K-major, fused block tail)"; }
+extern "C" const char* gq_version(void) { return "grasp_qnet 0.5 sm_100a bf16 tcgen05 (persistent CTAs, both operands by TMA: im2col activations + tiled weights, SW128 K-major, double-buffered TMEM accumulator, fused block tail)"; }
 
-// tile shape: 128 output pixels x 64 / 128 / 256 output channels (the widest that divides Cout), 3 shared-memory stages so that two
-// CTAs share an SM at BLOCK_N <= 128 (r01 sweep with the v1 kernel, whole forward: BN<=128/ST4 179, BN<=128/ST3 214, BN<=256/ST4 206,
-// BN<=256/ST3 217 TFLOP/s).  Tuning overrides: GQ_BN=128, GQ_ST=4, GQ_NPW=4 (producer warps, default 8), GQ_CGB=1 (weights bypass L1), GQ_TMA=0 (weight tiles by cp.async instead of TMA), GQ_KERNEL=1 (first kernel version).
-struct ConvCfg { int bn, nst, kernel, npw, cg, tma, persist; };
+// tile shape: 128 output pixels x 64 / 128 / 256 output channels (the widest that divides Cout).  Tuning overrides: GQ_BN=128,
+// GQ_PERSIST=0 (non-persistent kernel: 3 stages, GQ_NPW=4|8 producer warps, GQ_CGB=1 weights bypass L1, GQ_TMA=0 weight tiles by cp.async).
+struct ConvCfg { int bn, npw, cg, tma, persist; };
 static ConvCfg conv_cfg(int Cout) {
-  static int env_bn = -1, env_st = -1, env_k = -1, env_npw = 8, env_cg = 0, env_tma = 1, env_persist = 0;
+  static int env_bn = -1, env_npw = 8, env_cg = 0, env_tma = 1, env_persist = 2;
   if (env_bn < 0) {
     const char* e = getenv("GQ_BN"); env_bn = e ? atoi(e) : 0;
-    e = getenv("GQ_ST"); env_st = e ? atoi(e) : 0;
-    e = getenv("GQ_KERNEL"); env_k = e ? atoi(e) : 2;
     e = getenv("GQ_NPW"); env_npw = (e && atoi(e) == 4) ? 4 : 8;  // r01i sweep, whole forward: 4 warps 366, 8 warps 381 TFLOP/s
     e = getenv("GQ_CGB"); env_cg = (e && atoi(e) != 0) ? 1 : 0;
-    e = getenv("GQ_PERSIST"); env_persist = e ? atoi(e) : 0;  // experimental persistent kernels (never run in round 1): 1 cp.async + TMA, 2 TMA only
+    e = getenv("GQ_PERSIST"); env_persist = (e && atoi(e) == 0) ? 0 : 2;  // r02a: persistent TMA kernel 477, non-persistent 439 TFLOP/s
     e = getenv("GQ_TMA"); env_tma = (e && atoi(e) == 0) ? 0 : 1;  // r01k: weight tiles by TMA 439 vs 414 TFLOP/s whole forward
   }
   ConvCfg c;
   c.bn = (Cout % 128 == 0) ? 128 : 64;
   if (env_bn != 128 && Cout % 256 == 0) c.bn = 256;
-  c.nst = env_st == 4 ? 4 : 3;
-  c.kernel = env_k == 1 ? 1 : 2;
   c.npw = env_npw; c.cg = env_cg; c.tma = env_tma; c.persist = env_persist;
-  if (c.kernel == 2) c.nst = 3;  // the second kernel is built with 3 stages only (4 measured slower, profiles/r01i_qnet_sweep.txt)
   return c;
 }
 static size_t conv_smem(int bn, int nst) { return (size_t)nst * (BM * BK * 2) + (size_t)nst * ((size_t)bn * BK * 2) + 8 * (2 * nst + 1) + 16; }
@@ -1061,21 +835,19 @@ static int launch_conv(const ConvCfg& c, dim3 grid, cudaStream_t st, const bf16*
     tma = false;
   }
   if (c.persist && tma) {
-    // experimental: one CTA per SM, static tile list, 192 KB of stages (4 / 6 / 8 at BLOCK_N 256 / 128 / 64)
+    // one CTA per SM, static tile list, 192 KB of stages (4 / 6 / 8 at BLOCK_N 256 / 128 / 64)
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int gx = (int)grid.x, gy = (int)grid.y, ntiles = gx * gy * (int)grid.z;
     const int nctas = ntiles < sms ? ntiles : sms;
-#define LAUNCH_P(BN_, ST_)                                                                                                           \
-  do {                                                                                                                               \
-    const size_t psmem = (size_t)ST_ * (BM * BK * 2 + BN_ * BK * 2) + 8 * (2 * ST_ + 4) + 16;                                         \
-    QCK(cudaFuncSetAttribute(k_conv_tc_persist<BN_, ST_, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));             \
-    k_conv_tc_persist<BN_, ST_, EPI><<<nctas, 416, psmem, st>>>(tm, x, bias, y, partials, resid, ss, out, H, W, Cin, Cout, ks, gx, gy, ntiles); \
-  } while (0)
-    if (c.persist == 2) {
-      alignas(64) CUtensorMap tmx;
-      if (make_act_tmap_im2col(&tmx, x, (int)grid.z, H, W, Cin, ks)) return -3;
+    alignas(64) CUtensorMap tmx;
+    static bool im2col_ok = true;
+    if (im2col_ok && make_act_tmap_im2col(&tmx, x, (int)grid.z, H, W, Cin, ks) != 0) {
+      im2col_ok = false;
+      fprintf(stderr, "grasp_qnet: %s; using the non-persistent kernel\n", q_err);
+    }
+    if (im2col_ok) {
 #define LAUNCH_T(BN_, ST_)                                                                                                           \
   do {                                                                                                                               \
     const size_t psmem = (size_t)ST_ * (BM * BK * 2 + BN_ * BK * 2) + 8 * (2 * ST_ + 4) + 16;                                         \
@@ -1088,11 +860,6 @@ static int launch_conv(const ConvCfg& c, dim3 grid, cudaStream_t st, const bf16*
 #undef LAUNCH_T
       return 0;
     }
-    if (c.bn == 256) LAUNCH_P(256, 4);
-    else if (c.bn == 128) LAUNCH_P(128, 6);
-    else LAUNCH_P(64, 8);
-#undef LAUNCH_P
-    return 0;
   }
 #define LAUNCH_ONE(BN_, NPW_, TMA_)                                                                                                  \
   do {                                                                                                                               \
@@ -1119,21 +886,8 @@ extern "C" int gq_conv_tc(const void* x, const void* w, const float* bias, float
   cudaStream_t st = (cudaStream_t)stream;
   const ConvCfg c = conv_cfg(Cout);
   dim3 grid((H * W + BM - 1) / BM, Cout / c.bn, B);
-  if (c.kernel == 1) {
-    const size_t smem = conv_smem(c.bn, c.nst);
-#define LAUNCH_V1(BN_, ST_)                                                                                                          \
-  do {                                                                                                                               \
-    QCK(cudaFuncSetAttribute(k_conv_tc_v1<BN_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                        \
-    k_conv_tc_v1<BN_, ST_><<<grid, 160, smem, st>>>((const bf16*)x, (const bf16*)w, bias, y, stats ? partials : nullptr, H, W, Cin, Cout, ks); \
-  } while (0)
-    if (c.bn == 256) { if (c.nst == 3) LAUNCH_V1(256, 3); else LAUNCH_V1(256, 4); }
-    else if (c.bn == 128) { if (c.nst == 3) LAUNCH_V1(128, 3); else LAUNCH_V1(128, 4); }
-    else { if (c.nst == 3) LAUNCH_V1(64, 3); else LAUNCH_V1(64, 4); }
-#undef LAUNCH_V1
-  } else {
-    int r = launch_conv<0>(c, grid, st, (const bf16*)x, (const bf16*)w, bias, y, stats ? partials : nullptr, nullptr, nullptr, nullptr, H, W, Cin, Cout, ks);
-    if (r) return r;
-  }
+  int r = launch_conv<0>(c, grid, st, (const bf16*)x, (const bf16*)w, bias, y, stats ? partials : nullptr, nullptr, nullptr, nullptr, H, W, Cin, Cout, ks);
+  if (r) return r;
   if (stats) k_bn_reduce<<<(B * Cout + 127) / 128, 128, 0, st>>>(partials, stats, B, (int)grid.x * 4, Cout);
   QCK(cudaGetLastError());
   return 0;
