@@ -128,37 +128,44 @@ __device__ __forceinline__ int group_exscan(int v, int lane, int& total) {
   return off - v;
 }
 #else
-__device__ __forceinline__ void gsync() { __syncthreads(); }
+// __syncthreads() is an ALIGNED barrier: every warp has to arrive converged.  The code in front of a group barrier often ends in
+// branches on values that are equal across the lanes only mathematically (MPR iterations, Newton / line-search exits), after which
+// the hardware may still run the lanes of a warp separately - r02d: "illegal instruction" at >= 160 envs, found by synccheck.  So every
+// group barrier first reconverges its warp.
+__device__ __forceinline__ void cta_sync() { __syncwarp(); __syncthreads(); }
+__device__ __forceinline__ void gsync() { cta_sync(); }
 // fixed order: butterfly inside each warp, then warp 0 .. GE_NW-1 (deterministic)
 __device__ __forceinline__ double group_sum(double v) {
   __shared__ double red[GE_NW];
+  __syncwarp();
   v = warp_sum(v);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
+  cta_sync();
   double s = red[0];
 #pragma unroll
   for (int w = 1; w < GE_NW; w++) s += red[w];
-  __syncthreads();
+  cta_sync();
   return s;
 }
 __device__ __forceinline__ double group_max(double v) {
   __shared__ double red[GE_NW];
+  __syncwarp();
   v = warp_max(v);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
+  cta_sync();
   double s = red[0];
 #pragma unroll
   for (int w = 1; w < GE_NW; w++) s = fmax(s, red[w]);
-  __syncthreads();
+  cta_sync();
   return s;
 }
-__device__ __forceinline__ bool group_any(bool p) { return __syncthreads_or(p ? 1 : 0) != 0; }
+__device__ __forceinline__ bool group_any(bool p) { __syncwarp(); return __syncthreads_or(p ? 1 : 0) != 0; }
 __device__ __forceinline__ int group_bcast_int(int v, int lane) {
   __shared__ int b;
   if (lane == 0) b = v;
-  __syncthreads();
+  cta_sync();
   int r = b;
-  __syncthreads();
+  cta_sync();
   return r;
 }
 __device__ __forceinline__ int group_exscan(int v, int lane, int& total) {
@@ -168,11 +175,11 @@ __device__ __forceinline__ int group_exscan(int v, int lane, int& total) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(FULL, off, o); if (wl >= o) off += u; }
   if (wl == 31) wsum[wid] = off;
-  __syncthreads();
+  cta_sync();
   int before = 0, tot = 0;
 #pragma unroll
   for (int w = 0; w < GE_NW; w++) { if (w < wid) before += wsum[w]; tot += wsum[w]; }
-  __syncthreads();
+  cta_sync();
   total = tot;
   return before + off - v;
 }

@@ -79,9 +79,9 @@ __device__ __forceinline__ unsigned long long group_bcast_u64(unsigned long long
 #else
   __shared__ unsigned long long b;
   if (lane == 0) b = v;
-  __syncthreads();
+  cta_sync();
   unsigned long long r = b;
-  __syncthreads();
+  cta_sync();
   return r;
 #endif
 }
@@ -112,13 +112,19 @@ __global__ void __launch_bounds__(256) k_run(EnvArrays E, int n_env, int nsub, i
       t = group_bcast_u64(t, lane);
       if (t >= total) { exhausted = true; break; }
       const int e = (int)(t % (unsigned long long)n_env), v = (int)(t / (unsigned long long)n_env);
-      if (!env_is_busy(E, e)) continue;
+      // ONE thread looks at the env's flags and takes the lock, the group follows its verdict: the flags change under our feet when
+      // another group finishes a visit of this env, and threads that read them separately (the four warps of a CTA-per-env group do
+      // so at different times) would part ways - r02d: illegal instruction / illegal address at >= 300 envs
       int got = 0;
-      if (lane == 0) got = atomicCAS(E.lock + e, 0, 1) == 0;
+      if (lane == 0 && env_is_busy(E, e) && atomicCAS(E.lock + e, 0, 1) == 0) {
+        // an earlier visit of this env still running elsewhere fails the CAS: this visit is dropped, never waited for
+        __threadfence();
+        if (env_is_busy(E, e)) got = 1;
+        else atomicExch(E.lock + e, 0);
+      }
       got = group_bcast_int(got, lane);
-      if (!got) continue;  // an earlier visit of this env is still running elsewhere: this visit is dropped, never waited for
+      if (!got) continue;
       __threadfence();
-      if (!env_is_busy(E, e)) { gsync(); if (lane == 0) atomicExch(E.lock + e, 0); continue; }
 #if GE_WS_IN_HBM
       ws = E.gws + (size_t)e * (L.total_bytes / 8);
 #endif
@@ -127,8 +133,9 @@ __global__ void __launch_bounds__(256) k_run(EnvArrays E, int n_env, int nsub, i
       env = e; running = true;
       left = nsub - v * quota < quota ? nsub - v * quota : quota;
     }
+    __syncwarp();
     if (!__syncthreads_or(env >= 0)) break;
-    if (env < 0) { stage_barriers_idle(stage_sync != 0); continue; }
+    if (env < 0) { stage_barriers_idle((stage_sync & 1) != 0); continue; }
     bool stepped = false;
     // one iteration of the reference loop that ends in a physics step (or the env going idle)
     while (true) {
@@ -139,13 +146,13 @@ __global__ void __launch_bounds__(256) k_run(EnvArrays E, int n_env, int nsub, i
       double delta = pid_and_delta(ws, lane, r.c.mask, c_m.timestep);
       if (delta < r.c.tol) { r.c.result = 1; r.c.reached = 1; }
       if (r.c.steps > r.c.maxsteps) { r.c.result = 2; r.c.active = 0; continue; }
-      sim_step(ws, wi, lane, &r.status, stage_sync != 0);
+      if (!(stage_sync & 0x100)) sim_step(ws, wi, lane, &r.status, (stage_sync & 1) != 0);  // bit 8: GE_DBG_NOSTEP (scheduler-only experiments)
       stepped = true;
       r.c.steps++; r.nstep++;
       if (r.c.reached) r.c.active = 0;
       break;
     }
-    if (!stepped) stage_barriers_idle(stage_sync != 0);
+    if (!stepped) stage_barriers_idle((stage_sync & 1) != 0);
     if (--left <= 0 || !running) {
       // a movement that just ended inside the last iteration still has to hand over to the program (no sub-step involved)
       while (!r.c.active && r.p.phase != PH_NONE) { if (!prog_advance(r.p, r.c, ws, lane, base, r.info, &r.reward)) break; }
@@ -535,6 +542,7 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
   h->stage_sync = h->lay.ws_global ? 0 : 1;  // lock-step CTAs pay off for the small scene only (equal work per env, code-fetch bound)
   if (const char* ev = getenv("GE_STAGE_SYNC")) h->stage_sync = atoi(ev) != 0;
   if (GE_NW > 1) h->stage_sync = 0;
+  if (const char* ev = getenv("GE_DBG_NOSTEP")) if (atoi(ev) != 0) h->stage_sync |= 0x100;
   if (const char* ev = getenv("GE_WPB")) if (GE_NW == 1) { int v = atoi(ev); if (v >= 1 && v <= 8 && (h->lay.ws_global || v * h->lay.total_bytes <= 227 * 1024)) h->wpb = v; }
   h->ws_smem = h->lay.ws_global ? 0 : (size_t)h->lay.total_bytes;
   if (h->ws_smem) {
@@ -561,6 +569,7 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_run, GE_LANES * h->wpb, (size_t)h->wpb * h->ws_smem));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     h->max_ctas = per_sm * sms > 0 ? per_sm * sms : 1;
+    if (const char* ev = getenv("GE_MAXCTAS")) { int v = atoi(ev); if (v >= 1 && v < h->max_ctas) h->max_ctas = v; }  // experiments: fewer resident CTAs
   }
   E.gws = nullptr;
   if (h->lay.ws_global) { AL(E.gws, double, N * (size_t)(h->lay.total_bytes / 8)); }
