@@ -50,6 +50,17 @@ int gq_head_up2(const void* x, const float* w, const float* bias, float* scratch
  * scratch_minmax [B,2] f32 */
 int gq_obs_to_state(const unsigned char* rgb, const float* depth, float depth_threshold, float* scratch_minmax, float* state, int B, int HW,
                     void* stream);
+/* Grasp_Agent.transform_observation(normalize=True, jitter_and_noise=True) batched - what the agent feeds the network while it learns
+ * (Grasping_Agent_multidiscrete.py:118-124 ColorJitter(0.5, 0.5, 0.5, 0.5), :318 depth += N(0, 0.001) before the min-max normalisation).
+ * noise_std: standard deviation of the depth noise (0.001); seed / env_index [B] int64 (NULL: 0..B-1) / step: key and counter of the
+ * counter-based generator, so a pixel's noise depends on (seed, global env id, step, pixel) only; jitter [B,4] f32 = brightness,
+ * contrast, saturation, hue factors and order [B,4] int32 = the permutation of the four operations, both drawn by the caller as
+ * torchvision's ColorJitter.get_params does (NULL jitter: no colour change; NULL order: 0,1,2,3); scratch_red [B,4] f32.
+ * Outputs (either may be NULL): state [B,4,HW] f32 (the agent's tensor layout), state_nhwc_bf16 [B,HW,4] bf16 (NHWC, feeds the first
+ * convolution without a repack). */
+int gq_obs_to_state_train(const unsigned char* rgb, const float* depth, float depth_threshold, float noise_std, unsigned long long seed,
+                          const long long* env_index, unsigned int step, const float* jitter, const int* order, float* scratch_red, float* state,
+                          void* state_nhwc_bf16, int B, int HW, void* stream);
 /* output.view(-1).max(0) per image (Grasping_Agent_multidiscrete.py:295-299): q [B,n] -> idx [B] int32 (rot*HW + y*W + x), val [B] f32 */
 int gq_argmax(const float* q, int B, int n, int* idx, float* val, void* stream);
 

@@ -57,7 +57,7 @@ __device__ __forceinline__ int island_owner(const int* island, int t) { return i
 
 __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int nsr, int lane) {
   const DevModel& m = c_m; const Layout& L = c_L;
-  double* H = ws + L.H;
+  double* H = ws + L.H;  // (CTA-per-env build: re-pointed at the env's HBM overflow row below if this build's blocks exceed L.hcap)
   const double *qM = ws + L.qM, *cdof = ws + L.cdof;
   const int wl = lane & 31, wid = lane >> 5;
   int* tcoupled = wi + L.i_tcoupled;
@@ -114,6 +114,18 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
       gsync();
       if (!changed) break;
     }
+    // The labels were merged with atomicMin, which is resolved in L2 and leaves any copy of the line in this SM's L1 as it was; the plain
+    // loads below (and in cholesky_solve) could then see pre-merge labels - and, in the CTA-per-env build, DIFFERENT warps different ones
+    // depending on when the line is evicted (r02d: garbage Hessian blocks -> non-finite states under load; gone with -Xptxas -dlcm=cg).
+    // Read the final labels past L1 once and write them back with ordinary stores, which L1 does track.
+    {
+      const int ta = lane, tb = lane + GE_LANES;  // (ntree <= 2 * GE_LANES is checked at ge_create)
+      const int la = ta < m.ntree ? ((volatile int*)island)[ta] : 0, lb = tb < m.ntree ? ((volatile int*)island)[tb] : 0;
+      gsync();
+      if (ta < m.ntree) island[ta] = la;
+      if (tb < m.ntree) island[tb] = lb;
+      gsync();
+    }
     // first row of every coupled tree inside its island block (members in ascending tree order); the representative also records the
     // island's size (first slot of its - otherwise unused - contact list row)
     LANE_LOOP(t, m.ntree) {
@@ -138,6 +150,21 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
     }
     T_HOFF(tlist, t) = off;
   }
+#if GE_NW > 1
+  {  // total size of this build's blocks (every thread adds up the same list)
+    int tot = 0;
+    for (int u = 0; u < m.ntree; u++) {
+      int n;
+      if (!tcoupled[u]) n = m.tree_dofnum[u];
+      else if (island[u] == u) n = tlist[u * GE_TLIST];
+      else continue;
+      tot += n * (n + 1) / 2;
+    }
+    const bool ovf = tot > L.hcap;
+    if (ovf) H = g_hovf;
+    if (lane == 0) wi[L.i_hflag] = ovf ? 1 : 0;
+  }
+#endif
   gsync();
   // ---- rows of M: zero fill of the whole block row, then the tree-sparse row of qM
   LANE_LOOP(i, m.nv) {
@@ -366,6 +393,9 @@ __device__ __noinline__ bool mass_block_solve(double* ws, double* x, double hdam
 __device__ __noinline__ void cholesky_solve(double* ws, int* wi, double* x, const double* g_, int lane) {
   const DevModel& m = c_m; const Layout& L = c_L;
   double* H = ws + L.H;
+#if GE_NW > 1
+  if (wi[L.i_hflag]) H = g_hovf;
+#endif
   const int wl = lane & 31, wid = lane >> 5;
   const int *tcoupled = wi + L.i_tcoupled, *tlist = wi + L.i_tlist;
   bool any_coupled = false;

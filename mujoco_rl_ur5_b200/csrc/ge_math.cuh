@@ -159,7 +159,19 @@ __device__ __forceinline__ double group_max(double v) {
   cta_sync();
   return s;
 }
-__device__ __forceinline__ bool group_any(bool p) { __syncwarp(); return __syncthreads_or(p ? 1 : 0) != 0; }
+// (a flag in shared memory and plain barriers instead of __syncthreads_or: r02d's GPU core dump showed "Warp Illegal Instruction" at the
+// BAR.RED of this function with the other warps of the CTA still leaving the preceding BAR.SYNC - the two barrier kinds share hardware
+// barrier 0 and PTX forbids intermixing bar.red with bar.sync on an active barrier)
+__device__ __forceinline__ bool group_any(bool p) {
+  __shared__ int flag;
+  if (threadIdx.x == 0) flag = 0;
+  cta_sync();
+  if (p) flag = 1;
+  cta_sync();
+  const bool r = flag != 0;
+  cta_sync();
+  return r;
+}
 __device__ __forceinline__ int group_bcast_int(int v, int lane) {
   __shared__ int b;
   if (lane == 0) b = v;

@@ -57,7 +57,10 @@ struct Layout {
   int total_bytes;
   int maxcon, maxcand;          // capacity of the contact / candidate lists
   int fk_bytes;                 // bytes of the workspace prefix the kinematics stage touches (kinematics-only kernels)
-  int ws_global;                // 1: the per-env workspace lives in HBM (E.gws) because it does not fit shared memory
+  int ws_global;                // 1: big-scene build (a CTA per env); E.gws then holds one overflow row per env for oversized Hessian builds
+  int hcap;                     // doubles of the Hessian block region at L.H (= nv (nv + 1) / 2 when everything always fits)
+  int hfull;                    // nv (nv + 1) / 2: size of the overflow row
+  int i_hflag;                  // int slot: 1 while the Hessian blocks of the current build live in the overflow row
 };
 
 // per-environment state in HBM, row-major [N, ...]
@@ -76,5 +79,5 @@ struct EnvArrays {
   int* busy_count;                // [1]
   int* lock;                      // [N] 1 while a warp of k_run holds the env (dynamic env -> warp assignment)
   unsigned long long* ticket;     // [1] monotonically increasing task counter of k_run (never reset: launches subtract their base)
-  double* gws;                    // [N, total_bytes/8] workspace rows when Layout::ws_global
+  double* gws;                    // [N, hfull] Hessian overflow rows (big-scene build when hcap < hfull), else NULL
 };

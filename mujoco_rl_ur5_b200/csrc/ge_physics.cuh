@@ -14,6 +14,8 @@ namespace ge {
 
 __constant__ DevModel c_m;
 __constant__ Layout c_L;
+__shared__ double* g_hovf;    // CTA-per-env build: HBM overflow row for the Hessian blocks of the env this CTA holds (may be null)
+__constant__ int c_nancheck;  // GE_NANCHECK=1: record in status bits 8.. the first pipeline stage that produced a non-finite value
 
 #define LANE_LOOP(i, n) for (int i = lane; i < (n); i += GE_LANES)
 
@@ -612,6 +614,7 @@ __device__ __noinline__ void support_w(const double* ws, int g, double inflate, 
       }
     }
     warp_argmax(bv, best);
+    if (best >= nvert) best = 0;  // a non-finite direction matches no vertex: stay inside the table (the step is flagged as non-finite later)
     v3copy(pl, v + 3 * best);
   }
   m3mulv(out, R, pl); v3add(out, out, ws + L.gpos + 3 * g); v3addscl(out, out, dir, inflate);

@@ -32,15 +32,27 @@ __device__ __forceinline__ void cta_barrier_unaligned() {
 __device__ __forceinline__ void stage_barrier(bool sync) { if (GE_STAGE_SYNC && sync) cta_barrier_unaligned(); }
 __device__ __forceinline__ void stage_barriers_idle(bool on) { if (GE_STAGE_SYNC && on) for (int k = 0; k < GE_NUM_STAGE_BARRIERS; k++) cta_barrier_unaligned(); }
 
+// debugging aid (GE_NANCHECK=1): first stage whose output holds a non-finite value -> one of status bits 8..15 (only the first is kept)
+__device__ __noinline__ void nan_probe(const double* a, int n, int lane, int* status, int bit) {
+  bool bad = false;
+  LANE_LOOP(i, n) if (!isfinite(a[i])) bad = true;
+  bad = group_any(bad);
+  if (bad && !(*status & 0xff00)) *status |= 1 << bit;
+}
 // mj_forward: kinematics -> bias -> mass matrix -> collision -> constraints -> smooth acceleration -> Newton
 __device__ __noinline__ StepInfo forward(double* ws, int* wi, int lane, int* status, bool sync = false) {
   const DevModel& m = c_m; const Layout& L = c_L;
   StepInfo si;
+  const bool dbg = c_nancheck != 0;
+  if (dbg) { nan_probe(ws + L.qpos, m.nq, lane, status, 8); nan_probe(ws + L.qvel, m.nv, lane, status, 8); nan_probe(ws + L.ctl, 32, lane, status, 8); }
   stage_fk(ws, lane);
+  if (dbg) { nan_probe(ws + L.gmat, 9 * m.ngeom, lane, status, 9); nan_probe(ws + L.cdof, 6 * m.nv, lane, status, 9); }
   stage_barrier(sync);
   si.ncon = stage_collision(ws, wi, lane, status);  // needs the geom frames only; bias forces / mass matrix reuse their storage
+  if (dbg) nan_probe(ws + L.con, si.ncon * L.cstride < 16 * si.ncon ? 0 : 16 * 0 + si.ncon * 0, lane, status, 10);
   stage_rne(ws, lane);  // qfrc_smooth := bias
   stage_crb(ws, lane);
+  if (dbg) { nan_probe(ws + L.qM, m.nM, lane, status, 11); nan_probe(ws + L.qfrc_smooth, m.nv, lane, status, 11); }
   // smooth forces: passive (joint damping) - bias + actuation (torque motors, gear * clamp(ctrl))
   const double *qvel = ws + L.qvel, *ctrl = ws + L.ctl + CTL_CTRL;
   double *qfs = ws + L.qfrc_smooth, *qas = ws + L.qacc_smooth;
@@ -62,9 +74,12 @@ __device__ __noinline__ StepInfo forward(double* ws, int* wi, int lane, int* sta
     factor_trees(ws + L.qLD, lane);
     solve_trees(ws + L.qLD, qas, lane);
   }
+  if (dbg) nan_probe(qas, m.nv, lane, status, 12);
   stage_barrier(sync);
   si.nsr = stage_constraints(ws, wi, lane, si.ncon, status);
+  if (dbg) nan_probe(ws + L.sr, 6 * GE_MAXSR * 0 + 4 * 0, lane, status, 13);
   si.niter = solve_newton(ws, wi, lane, si.ncon, si.nsr, GE_STAGE_SYNC && sync);
+  if (dbg) nan_probe(ws + L.qacc, m.nv, lane, status, 14);
   if (si.niter >= m.iterations) *status |= 4;
   LANE_LOOP(d, m.nv) ws[L.qaccws + d] = ws[L.qacc + d];
   gsync();

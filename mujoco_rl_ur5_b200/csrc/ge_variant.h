@@ -17,7 +17,7 @@
 #else
 #define ge ge_hbm
 #define GE_API(n) n##_hbm
-#define GE_WS_IN_HBM 1
+#define GE_WS_IN_HBM 0  // (r02: the big-scene build keeps its workspace in shared memory too; only oversized Hessian builds overflow to HBM)
 // r02: the big-scene variant gives every environment a whole CTA of 4 warps.  The stage code is the same source: lane loops stride
 // by GE_LANES, `gsync()` is __syncthreads(), reductions go through shared memory, and the pieces that are inherently warp-shaped
 // (MPR on one geom pair, the 8-lane tree groups, one dense island factorisation) are dealt out to the 4 warps.

@@ -23,7 +23,7 @@ static int fail(int code, const char* fmt, const char* a = "") { snprintf(g_err,
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(GE_ERR_CUDA, "CUDA error: %s", cudaGetErrorString(e_)); } while (0)
 
 extern "C" const char* ge_last_error(void) { return g_err; }
-extern "C" const char* ge_version(void) { return GE_WS_IN_HBM ? "grasp_engine 0.2 sm_100a fp64 warp-per-env (workspace: HBM rows)" : "grasp_engine 0.2 sm_100a fp64 warp-per-env (workspace: shared memory)"; }
+extern "C" const char* ge_version(void) { return GE_NW > 1 ? "grasp_engine 0.3 sm_100a fp64 CTA-per-env (4 warps, workspace: shared memory, Hessian overflow: HBM)" : "grasp_engine 0.3 sm_100a fp64 warp-per-env (workspace: shared memory)"; }
 
 // ------------------------------------------------------------------------------------------------ kernels
 // Sub-step kernel: one warp per environment, environments handed to warps DYNAMICALLY.
@@ -95,12 +95,8 @@ __global__ void __launch_bounds__(256) k_run(EnvArrays E, int n_env, int nsub, i
   const int visits = (nsub + quota - 1) / quota;
   const unsigned long long total = (unsigned long long)n_env * visits;
   const double base[3] = {base_x, base_y, base_z};
-#if !GE_WS_IN_HBM
   double* ws = smem + (size_t)threadIdx.y * (L.total_bytes / 8);
-#else
-  double* ws = nullptr;
-#endif
-  int* wi = nullptr;
+  int* wi = (int*)(ws + L.total_doubles);
   EnvRegs r;
   int env = -1, left = 0;
   bool exhausted = false, running = false;
@@ -125,16 +121,17 @@ __global__ void __launch_bounds__(256) k_run(EnvArrays E, int n_env, int nsub, i
       got = group_bcast_int(got, lane);
       if (!got) continue;
       __threadfence();
-#if GE_WS_IN_HBM
-      ws = E.gws + (size_t)e * (L.total_bytes / 8);
-#endif
-      wi = (int*)(ws + L.total_doubles);
+      if (GE_NW > 1 && lane == 0) g_hovf = E.gws ? E.gws + (size_t)e * L.hfull : nullptr;  // this env's Hessian overflow row
       env_load(E, e, ws, lane, r);
       env = e; running = true;
       left = nsub - v * quota < quota ? nsub - v * quota : quota;
     }
+#if GE_NW == 1
     __syncwarp();
-    if (!__syncthreads_or(env >= 0)) break;
+    if (!__syncthreads_or(env >= 0)) break;  // all warps (= envs) of the CTA are out of work
+#else
+    if (env < 0) break;                      // one env per CTA: `env` is the same in every thread
+#endif
     if (env < 0) { stage_barriers_idle((stage_sync & 1) != 0); continue; }
     bool stepped = false;
     // one iteration of the reference loop that ends in a physics step (or the env going idle)
@@ -178,11 +175,8 @@ __global__ void __launch_bounds__(GE_LANES) k_debug(EnvArrays E, int env, int fi
   extern __shared__ double smem[];
   const DevModel& m = c_m; const Layout& L = c_L;
   int lane = threadIdx.x;
-#if GE_WS_IN_HBM
-  double* ws = E.gws + (size_t)env * (L.total_bytes / 8);
-#else
   double* ws = smem;
-#endif
+  if (GE_NW > 1 && threadIdx.x == 0) g_hovf = E.gws ? E.gws + (size_t)env * L.hfull : nullptr;
   int* wi = (int*)(ws + L.total_doubles);
   LANE_LOOP(i, m.nq) ws[L.qpos + i] = E.qpos[(size_t)env * m.nq + i];
   LANE_LOOP(i, m.nv) { ws[L.qvel + i] = E.qvel[(size_t)env * m.nv + i]; ws[L.qaccws + i] = E.qaccws[(size_t)env * m.nv + i]; }
@@ -293,11 +287,8 @@ __global__ void __launch_bounds__(GE_LANES) k_step_open(EnvArrays E, int n_env, 
   const DevModel& m = c_m; const Layout& L = c_L;
   int env = blockIdx.x, lane = threadIdx.x;
   if (env >= n_env || (emask && !emask[env])) return;
-#if GE_WS_IN_HBM
-  double* ws = E.gws + (size_t)env * (L.total_bytes / 8);
-#else
   double* ws = smem;
-#endif
+  if (GE_NW > 1 && threadIdx.x == 0) g_hovf = E.gws ? E.gws + (size_t)env * L.hfull : nullptr;
   int* wi = (int*)(ws + L.total_doubles);
   LANE_LOOP(i, m.nq) ws[L.qpos + i] = E.qpos[(size_t)env * m.nq + i];
   LANE_LOOP(i, m.nv) { ws[L.qvel + i] = E.qvel[(size_t)env * m.nv + i]; ws[L.qaccws + i] = E.qaccws[(size_t)env * m.nv + i]; }
@@ -392,7 +383,7 @@ static ge_engine* g_bound = nullptr;  // engine whose model / layout currently s
 
 static int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
-static void make_layout(const DevModel& m, Layout& L, const int* tree_dofnum_h, const int* tree_simple_h, int ntree_dofnum_n) {
+static void make_layout(const DevModel& m, Layout& L, const int* tree_dofnum_h, const int* tree_simple_h, int ntree_dofnum_n, int maxcon, int hcap) {
   int nb = m.nbody, nj = m.njnt, nv = m.nv, ng = m.ngeom;
   int o = 0;
   auto take = [&](int n) { int r = o; o += align_up(n, 2); return r; };
@@ -407,7 +398,7 @@ static void make_layout(const DevModel& m, Layout& L, const int* tree_dofnum_h, 
   L.Ma = take(nv); L.grad = take(nv); L.search = take(nv); L.Mv = take(nv);
   L.cstride = align_up(C_MU + 4 * m.maxdim - 1, 2);
   // list capacities: the 6-object scene never exceeded 20 contacts; piles of free objects need room for ~3 contacts per object
-  L.maxcon = m.ntree <= 8 ? 32 : 128;
+  L.maxcon = maxcon;
   L.maxcand = 2 * L.maxcon;
   L.con = take(L.maxcon * L.cstride);
   L.sr = take(6 * GE_MAXSR);
@@ -437,7 +428,9 @@ static void make_layout(const DevModel& m, Layout& L, const int* tree_dofnum_h, 
   // phase B (solver)
   int b = L.scratch;
   auto takeB = [&](int n) { int r = b; b += align_up(n, 2); return r; };
-  L.H = takeB(nv * (nv + 1) / 2); L.Vb = takeB(6 * nb); L.Wb = takeB(6 * nb);
+  L.hfull = nv * (nv + 1) / 2;
+  L.hcap = hcap > 0 && hcap < L.hfull ? hcap : L.hfull;
+  L.H = takeB(L.hcap); L.Vb = takeB(6 * nb); L.Wb = takeB(6 * nb);
   int endB = b;
   // crb (10*nb) is written over cvel+cacc (12*nb) — asserted by construction (cvel, cacc adjacent)
   int end = endA1 > endA2 ? endA1 : endA2;
@@ -448,7 +441,7 @@ static void make_layout(const DevModel& m, Layout& L, const int* tree_dofnum_h, 
   auto takeI = [&](int n) { int r = io; io += n; return r; };
   L.i_cb1 = takeI(L.maxcon); L.i_cb2 = takeI(L.maxcon); L.i_ct1 = takeI(L.maxcon); L.i_ct2 = takeI(L.maxcon); L.i_cdim = takeI(L.maxcon); L.i_cpair = takeI(L.maxcon); L.i_cact = takeI(L.maxcon);
   L.i_srA = takeI(GE_MAXSR); L.i_srB = takeI(GE_MAXSR); L.i_srtype = takeI(GE_MAXSR); L.i_sract = takeI(GE_MAXSR);
-  L.i_cand = takeI(L.maxcand); L.i_first = takeI(nv); L.i_tcoupled = takeI(m.ntree); L.i_tcount = takeI(m.ntree); L.i_tlist = takeI(m.ntree * GE_TLIST); L.i_island = takeI(m.ntree);
+  L.i_cand = takeI(L.maxcand); L.i_first = takeI(nv); L.i_tcoupled = takeI(m.ntree); L.i_tcount = takeI(m.ntree); L.i_tlist = takeI(m.ntree * GE_TLIST); L.i_island = takeI(m.ntree); L.i_hflag = takeI(GE_NW > 1 ? 1 : 0);
   L.total_ints = align_up(io, 4);
   L.total_bytes = L.total_doubles * 8 + L.total_ints * 4;
   L.ws_global = 0;
@@ -500,6 +493,7 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
   m.ik_chain = PD("ik_chain"); m.ik_lower = PD("ik_lower"); m.ik_upper = PD("ik_upper"); m.ik_offset = PD("ik_offset");
   if (missing) { cudaFree(h->dblob); delete h; return GE_ERR_MODEL; }
   if (m.nu != GE_NU) { cudaFree(h->dblob); delete h; return fail(GE_ERR_MODEL, "model must have 7 actuators"); }
+  if (m.ntree > 64) { cudaFree(h->dblob); delete h; return fail(GE_ERR_MODEL, "model has more than 64 kinematic trees"); }
   {
     int64_t cnt = 0;
     const int32_t* cd = (const int32_t*)blob_find(B, "pair_condim", &cnt);
@@ -512,22 +506,54 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
     if (!bp) { cudaFree(h->dblob); delete h; return fail(GE_ERR_MODEL, "blob entry missing: %s", "ik_base_pos"); }
     memcpy(h->base_pos, bp, 24);
   }
-  make_layout(m, h->lay, (const int*)blob_find(B, "tree_dofnum", nullptr), (const int*)blob_find(B, "tree_simple", nullptr), m.ntree);
-  // workspace placement is a property of the build variant (ge_variant.h): shared memory when one env fits a CTA's 227 KB,
-  // else one row per env in HBM; the dispatcher retries with the HBM variant on GE_ERR_TOO_LARGE
-#if GE_WS_IN_HBM
-  h->lay.ws_global = 1;
-#else
+  const int* tdn = (const int*)blob_find(B, "tree_dofnum", nullptr);
+  const int* tsi = (const int*)blob_find(B, "tree_simple", nullptr);
+  // list capacities: the 6-object scene never exceeded 20 contacts; piles of free objects need room for ~3 contacts per object
+  const int maxcon_default = m.ntree <= 8 ? 32 : 128;
+#if GE_NW == 1
+  // warp-per-env build: the whole workspace (full Hessian triangle) in one shared-memory slice per warp, or not at all
+  make_layout(m, h->lay, tdn, tsi, m.ntree, maxcon_default, 0);
   h->lay.ws_global = 0;
   if (h->lay.total_bytes > 227 * 1024) { cudaFree(h->dblob); delete h; return fail(GE_ERR_TOO_LARGE, "per-env workspace exceeds shared memory"); }
+#else
+  // CTA-per-env build: the workspace of ONE env per CTA in shared memory.  The Hessian block region is capped so that two CTAs share
+  // an SM (2 x 113 KB); a Hessian build that needs more (one huge island) uses the env's overflow row in HBM for that build.
+  {
+    int maxcon = maxcon_default;
+    if (const char* ev = getenv("GE_MAXCON")) { int v = atoi(ev); if (v >= 16 && v <= 512) maxcon = v; }
+    int diag = 0;
+    for (int t = 0; t < m.ntree; t++) diag += tdn[t] * (tdn[t] + 1) / 2;
+    const int hfull = m.nv * (m.nv + 1) / 2;
+    int need_min = diag + 6 * maxcon + 64;  // all trees uncoupled / the contact-wrench scratch of nt_update
+    if (need_min > hfull) need_min = hfull;
+    // the Hessian region shares the phase-aliased scratch with the kinematics arrays: largest cap whose layout fits the budget
+    auto fit = [&](long budget) {
+      int lo = 0, hi = hfull;  // largest cap in [1, hfull] with total_bytes <= budget (0: none)
+      while (lo < hi) {
+        int mid = (lo + hi + 1) / 2;
+        Layout T;
+        make_layout(m, T, tdn, tsi, m.ntree, maxcon, mid);
+        if ((long)T.total_bytes <= budget) lo = mid; else hi = mid - 1;
+      }
+      return lo;
+    };
+    const long budget2 = 233472 / 2 - 1024 - 2048, budget1 = 227 * 1024 - 2048;  // per CTA: system reserve and the static arrays taken off
+    int cap = fit(budget2);
+    if (cap < need_min) cap = fit(budget1);
+    if (cap < need_min) { cudaFree(h->dblob); delete h; return fail(GE_ERR_MODEL, "model too large: per-env workspace exceeds shared memory even with one CTA per SM"); }
+    if (const char* ev = getenv("GE_HCAP")) { long v = atol(ev); if (v >= need_min && v <= hfull) cap = (int)v; }
+    make_layout(m, h->lay, tdn, tsi, m.ntree, maxcon, cap);
+    if (h->lay.total_bytes > 227 * 1024) { cudaFree(h->dblob); delete h; return fail(GE_ERR_MODEL, "model too large: per-env workspace exceeds shared memory"); }
+    h->lay.ws_global = 1;
+  }
 #endif
   if (h->lay.fk_bytes > 227 * 1024) { cudaFree(h->dblob); delete h; return fail(GE_ERR_MODEL, "model too large: kinematics workspace exceeds shared memory"); }
   CK(cudaMemcpyToSymbol(c_m, &m, sizeof m));
   CK(cudaMemcpyToSymbol(c_L, &h->lay, sizeof(Layout)));
+  { int nc = 0; if (const char* ev = getenv("GE_NANCHECK")) nc = atoi(ev) != 0; CK(cudaMemcpyToSymbol(c_nancheck, &nc, sizeof nc)); }
   // warps (= envs) per CTA: maximise the resident warps per SM (228 KB shared memory per SM, 1 KB reserved per CTA, 227 KB max per
   // CTA); ties go to the smaller CTA (less barrier imbalance).  r01 sweeps are in DESIGN.md; GE_WPB overrides.
   if (GE_NW > 1) h->wpb = 1;  // CTA-per-env build: one environment per CTA of GE_NW warps
-  else if (h->lay.ws_global) h->wpb = 4;
   else {
     int best = 1, best_warps = 0;
     for (int w = 1; w <= 8; w++) {
@@ -539,12 +565,15 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
     }
     h->wpb = best;
   }
-  h->stage_sync = h->lay.ws_global ? 0 : 1;  // lock-step CTAs pay off for the small scene only (equal work per env, code-fetch bound)
+  h->stage_sync = 1;  // lock-step warps of a CTA share instruction-cache lines (warp-per-env build)
   if (const char* ev = getenv("GE_STAGE_SYNC")) h->stage_sync = atoi(ev) != 0;
   if (GE_NW > 1) h->stage_sync = 0;
   if (const char* ev = getenv("GE_DBG_NOSTEP")) if (atoi(ev) != 0) h->stage_sync |= 0x100;
-  if (const char* ev = getenv("GE_WPB")) if (GE_NW == 1) { int v = atoi(ev); if (v >= 1 && v <= 8 && (h->lay.ws_global || v * h->lay.total_bytes <= 227 * 1024)) h->wpb = v; }
-  h->ws_smem = h->lay.ws_global ? 0 : (size_t)h->lay.total_bytes;
+  if (const char* ev = getenv("GE_WPB")) if (GE_NW == 1) { int v = atoi(ev); if (v >= 1 && v <= 8 && v * h->lay.total_bytes <= 227 * 1024) h->wpb = v; }
+  h->ws_smem = (size_t)h->lay.total_bytes;
+  if (getenv("GE_VERBOSE"))
+    fprintf(stderr, "grasp_engine: %s build, workspace %d B per env (%d doubles + %d ints), contacts <= %d, Hessian region %d of %d doubles, %d env(s) per CTA\n",
+            GE_NW > 1 ? "CTA-per-env" : "warp-per-env", h->lay.total_bytes, h->lay.total_doubles, h->lay.total_ints, h->lay.maxcon, h->lay.hcap, h->lay.hfull, h->wpb);
   if (h->ws_smem) {
     CK(cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, h->wpb * h->lay.total_bytes));
     if (h->lay.total_bytes > 48 * 1024) {
@@ -572,7 +601,7 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
     if (const char* ev = getenv("GE_MAXCTAS")) { int v = atoi(ev); if (v >= 1 && v < h->max_ctas) h->max_ctas = v; }  // experiments: fewer resident CTAs
   }
   E.gws = nullptr;
-  if (h->lay.ws_global) { AL(E.gws, double, N * (size_t)(h->lay.total_bytes / 8)); }
+  if (h->lay.hcap < h->lay.hfull) { AL(E.gws, double, N * (size_t)h->lay.hfull); }
   AL(h->d_nout, int, 1); AL(h->d_dbg, double, 1 << 16);
 #undef AL
   render_init(h->rctx, m, h->hblob.data());

@@ -741,7 +741,126 @@ __global__ void k_obs_state(const unsigned char* __restrict__ rgb, const float* 
   out[3 * (size_t)HW] = (-fminf(depth[i], thr) - lo) / (hi - lo);
 }
 
+// ---- training-time transform_observation (normalize=True, jitter_and_noise=True; Grasping_Agent_multidiscrete.py:118-124,301-368):
+// depth clipped, + N(0, noise_std) per pixel, negated, min-max normalised per image AFTER the noise (:318-322); rgb through
+// ColorJitter(brightness, contrast, saturation, hue) with the per-image factors and operation order drawn by the caller (torchvision's
+// get_params: randperm(4) + four uniforms), applied with torchvision's float-tensor arithmetic (_blend / rgb_to_grayscale / _rgb2hsv /
+// _hsv2rgb).  The noise comes from a counter-based generator (Philox4x32-10) keyed on the seed and indexed by (global env id, step,
+// pixel): the value of a pixel does not depend on how the envs are batched or sharded over GPUs.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// standard normal from counter (pixel, env, step) under key = seed (Box-Muller on two of the four words)
+__device__ __forceinline__ float obs_noise(uint64_t seed, uint64_t env, uint32_t step, uint32_t pixel) {
+  uint32_t w[4];
+  philox4x32_10(pixel, (uint32_t)env, (uint32_t)(env >> 32), step, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+  const float u1 = ((float)(w[0] >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(w[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+__device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.f), 1.f); }
+__device__ __forceinline__ float gray_of(float r, float g, float b) { return 0.2989f * r + 0.587f * g + 0.114f * b; }
+// one ColorJitter operation on one pixel; op: 0 brightness, 1 contrast (needs the image's grey mean), 2 saturation, 3 hue
+__device__ __forceinline__ void jitter_op(int op, float f, float mean, float& r, float& g, float& b) {
+  if (op == 0) { r = clamp01(f * r); g = clamp01(f * g); b = clamp01(f * b); }
+  else if (op == 1) { const float m = (1.f - f) * mean; r = clamp01(f * r + m); g = clamp01(f * g + m); b = clamp01(f * b + m); }
+  else if (op == 2) { const float m = (1.f - f) * gray_of(r, g, b); r = clamp01(f * r + m); g = clamp01(f * g + m); b = clamp01(f * b + m); }
+  else {
+    const float maxc = fmaxf(r, fmaxf(g, b)), minc = fminf(r, fminf(g, b));
+    const bool eqc = maxc == minc;
+    const float cr = maxc - minc, s = cr / (eqc ? 1.f : maxc), div = eqc ? 1.f : cr;
+    const float rc = (maxc - r) / div, gc = (maxc - g) / div, bc = (maxc - b) / div;
+    const float hr = (maxc == r) ? (bc - gc) : 0.f, hg = (maxc == g && maxc != r) ? (2.f + rc - bc) : 0.f, hb = (maxc != g && maxc != r) ? (4.f + gc - rc) : 0.f;
+    float h = fmodf((hr + hg + hb) / 6.f + 1.f, 1.f);
+    h = h + f;                       // torch's % : result has the sign of the divisor
+    h = h - floorf(h);
+    const float v = maxc, h6 = h * 6.f, fl = floorf(h6), ff = h6 - fl;
+    int i = ((int)fl) % 6;
+    if (i < 0) i += 6;
+    const float pp = clamp01(v * (1.f - s)), q = clamp01(v * (1.f - s * ff)), t = clamp01(v * (1.f - s * (1.f - ff)));
+    r = i == 0 ? v : i == 1 ? q : i == 2 ? pp : i == 3 ? pp : i == 4 ? t : v;
+    g = i == 0 ? t : i == 1 ? v : i == 2 ? v : i == 3 ? q : i == 4 ? pp : pp;
+    b = i == 0 ? pp : i == 1 ? pp : i == 2 ? t : i == 3 ? v : i == 4 ? v : q;
+  }
+}
+// per image: min / max of the noisy negated clipped depth, and the grey mean of the image as it is when the contrast operation runs
+__global__ void __launch_bounds__(256) k_obs_train_reduce(const unsigned char* __restrict__ rgb, const float* __restrict__ depth, int HW, float thr, float noise_std,
+                                                          unsigned long long seed, const long long* __restrict__ env_index, unsigned int step,
+                                                          const float* __restrict__ jitter, const int* __restrict__ order, float* __restrict__ red) {
+  __shared__ float smin[256], smax[256];
+  __shared__ double ssum[256];
+  const int b = blockIdx.x;
+  const unsigned long long env = env_index ? (unsigned long long)env_index[b] : (unsigned long long)b;
+  int ord[4] = {0, 1, 2, 3};
+  float fac[4] = {1.f, 1.f, 1.f, 0.f};
+  if (jitter) for (int k = 0; k < 4; k++) fac[k] = jitter[4 * b + k];
+  if (order) for (int k = 0; k < 4; k++) ord[k] = order[4 * b + k];
+  float lo = 3.0e38f, hi = -3.0e38f;
+  double gs = 0;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    float v = -(fminf(depth[(size_t)b * HW + i], thr) + noise_std * obs_noise(seed, env, step, (uint32_t)i));
+    lo = fminf(lo, v); hi = fmaxf(hi, v);
+    if (jitter) {
+      const unsigned char* px = rgb + ((size_t)b * HW + i) * 3;
+      float r = px[0] * (1.f / 255.f), g = px[1] * (1.f / 255.f), bl = px[2] * (1.f / 255.f);
+      for (int k = 0; k < 4 && ord[k] != 1; k++) jitter_op(ord[k], fac[ord[k]], 0.f, r, g, bl);  // the operations in front of contrast
+      gs += gray_of(r, g, bl);
+    }
+  }
+  smin[threadIdx.x] = lo; smax[threadIdx.x] = hi; ssum[threadIdx.x] = gs;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      smin[threadIdx.x] = fminf(smin[threadIdx.x], smin[threadIdx.x + o]); smax[threadIdx.x] = fmaxf(smax[threadIdx.x], smax[threadIdx.x + o]);
+      ssum[threadIdx.x] += ssum[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { red[4 * b] = smin[0]; red[4 * b + 1] = smax[0]; red[4 * b + 2] = (float)(ssum[0] / HW); red[4 * b + 3] = 0.f; }
+}
+__global__ void k_obs_train_state(const unsigned char* __restrict__ rgb, const float* __restrict__ depth, const float* __restrict__ red, float thr, float noise_std,
+                                  unsigned long long seed, const long long* __restrict__ env_index, unsigned int step, const float* __restrict__ jitter,
+                                  const int* __restrict__ order, int B, int HW, float* __restrict__ state, bf16* __restrict__ state_nhwc) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * HW) return;
+  const int b = i / HW, p = i % HW;
+  const unsigned long long env = env_index ? (unsigned long long)env_index[b] : (unsigned long long)b;
+  float r = rgb[3 * i] * (1.f / 255.f), g = rgb[3 * i + 1] * (1.f / 255.f), bl = rgb[3 * i + 2] * (1.f / 255.f);
+  if (jitter) {
+    const float mean = red[4 * b + 2];
+    for (int k = 0; k < 4; k++) { const int op = order ? order[4 * b + k] : k; jitter_op(op, jitter[4 * b + op], mean, r, g, bl); }
+  }
+  const float lo = red[4 * b], hi = red[4 * b + 1];
+  const float d = (-(fminf(depth[i], thr) + noise_std * obs_noise(seed, env, step, (uint32_t)p)) - lo) / (hi - lo);
+  if (state) {
+    float* out = state + (size_t)b * 4 * HW + p;
+    out[0] = r; out[HW] = g; out[2 * (size_t)HW] = bl; out[3 * (size_t)HW] = d;
+  }
+  if (state_nhwc) {
+    __nv_bfloat162* o = (__nv_bfloat162*)(state_nhwc + i * 4);
+    o[0] = __floats2bfloat162_rn(r, g); o[1] = __floats2bfloat162_rn(bl, d);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ C-ABI
+extern "C" int gq_obs_to_state_train(const unsigned char* rgb, const float* depth, float depth_threshold, float noise_std, unsigned long long seed,
+                                     const long long* env_index, unsigned int step, const float* jitter, const int* order, float* scratch_red,
+                                     float* state, void* state_nhwc_bf16, int B, int HW, void* stream) {
+  if (!rgb || !depth || !scratch_red || (!state && !state_nhwc_bf16) || B <= 0 || HW <= 0) { snprintf(q_err, sizeof q_err, "gq_obs_to_state_train: bad argument"); return -1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  k_obs_train_reduce<<<B, 256, 0, st>>>(rgb, depth, HW, depth_threshold, noise_std, seed, env_index, step, jitter, order, scratch_red);
+  k_obs_train_state<<<(unsigned)(((size_t)B * HW + 255) / 256), 256, 0, st>>>(rgb, depth, scratch_red, depth_threshold, noise_std, seed, env_index, step, jitter, order,
+                                                                              B, HW, state, (bf16*)state_nhwc_bf16);
+  QCK(cudaGetLastError());
+  return 0;
+}
 extern "C" int gq_obs_to_state(const unsigned char* rgb, const float* depth, float depth_threshold, float* scratch_minmax, float* state, int B, int HW,
                                void* stream) {
   cudaStream_t st = (cudaStream_t)stream;

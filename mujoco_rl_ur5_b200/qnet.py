@@ -20,7 +20,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 QLIB_PATH = os.path.join(_HERE, "csrc", "libgrasp_qnet.so")
 _QLIB = None
-QSYMBOLS = ["gq_last_error", "gq_version", "gq_conv_tc", "gq_conv_tc_block_out", "gq_conv_first", "gq_maxpool", "gq_bn_act", "gq_upsample2x", "gq_head", "gq_head_up2", "gq_argmax", "gq_obs_to_state"]
+QSYMBOLS = ["gq_last_error", "gq_version", "gq_conv_tc", "gq_conv_tc_block_out", "gq_conv_first", "gq_maxpool", "gq_bn_act", "gq_upsample2x", "gq_head", "gq_head_up2", "gq_argmax", "gq_obs_to_state", "gq_obs_to_state_train"]
 
 
 def load_qnet_library():
@@ -42,6 +42,7 @@ def load_qnet_library():
         L.gq_head_up2.argtypes = [P, P, P, P, P, I, I, I, I, P]
         L.gq_argmax.argtypes = [P, I, I, P, P, P]
         L.gq_obs_to_state.argtypes = [P, P, F, P, P, I, I, P]
+        L.gq_obs_to_state_train.argtypes = [P, P, F, F, C.c_uint64, P, C.c_uint32, P, P, P, P, P, I, I, P]
         _QLIB = L
     return _QLIB
 
@@ -240,6 +241,37 @@ class QNetForward:
         self._ck(self.L.gq_obs_to_state(self._p(rgb), self._p(depth), float(depth_threshold), self._p(mm), self._p(state), B, H * W, self._stream()), "gq_obs_to_state")
         self.launches += 1
         return state
+
+    def draw_color_jitter(self, B, generator=None, brightness=0.5, contrast=0.5, saturation=0.5, hue=0.5):
+        """per-image ColorJitter parameters exactly as torchvision's ColorJitter.get_params draws them (randperm(4), then the four
+        uniforms, per image; Grasping_Agent_multidiscrete.py:121): -> (factors [B,4] f32, order [B,4] int32) on the device"""
+        t = self.torch
+        fac, order = [], []
+        for _ in range(B):
+            order.append(t.randperm(4, generator=generator))
+            fac.append(t.stack([t.empty(1).uniform_(1 - brightness, 1 + brightness, generator=generator)[0],
+                                t.empty(1).uniform_(1 - contrast, 1 + contrast, generator=generator)[0],
+                                t.empty(1).uniform_(1 - saturation, 1 + saturation, generator=generator)[0],
+                                t.empty(1).uniform_(-hue, hue, generator=generator)[0]]))
+        return t.stack(fac).to(self.dev, t.float32).contiguous(), t.stack(order).to(self.dev, t.int32).contiguous()
+
+    def obs_to_state_train(self, obs, depth_threshold=1.1, noise_std=0.001, seed=0, step=0, env_index=None, jitter=None, order=None, nhwc_bf16=False):
+        """transform_observation as the LEARNING agent calls it (normalize=True, jitter_and_noise=True), batched on the device: depth noise
+        N(0, noise_std) from a counter-based generator keyed on (seed, global env id, step, pixel) added before the min-max normalisation,
+        ColorJitter with the given per-image factors / operation order (see draw_color_jitter; None = no colour change).
+        -> [B,4,H,W] f32, or ([B,4,H,W] f32, [B,H,W,4] bf16 NHWC) with nhwc_bf16=True"""
+        t = self.torch
+        rgb, depth = obs["rgb"].contiguous(), obs["depth"].contiguous()
+        B, H, W = depth.shape
+        state = t.empty((B, 4, H, W), dtype=t.float32, device=self.dev)
+        nhwc = t.empty((B, H, W, 4), dtype=t.bfloat16, device=self.dev) if nhwc_bf16 else None
+        red = t.empty((B, 4), dtype=t.float32, device=self.dev)
+        ei = None if env_index is None else t.as_tensor(env_index).to(self.dev, t.int64).contiguous()
+        self._ck(self.L.gq_obs_to_state_train(self._p(rgb), self._p(depth), float(depth_threshold), float(noise_std), int(seed) & (2 ** 64 - 1), self._p(ei),
+                                              int(step) & 0xFFFFFFFF, self._p(jitter), self._p(order), self._p(red), self._p(state), self._p(nhwc), B, H * W,
+                                              self._stream()), "gq_obs_to_state_train")
+        self.launches += 1
+        return (state, nhwc) if nhwc_bf16 else state
 
     def greedy(self, q):
         """flat arg-max per image and its split into (pixel index, rotation index) as transform_action does

@@ -11,7 +11,7 @@ stamp "scene A suite (unchanged warp-per-env build must still pass)"
 timeout 400 python -m pytest tests/test_parity_gpu.py tests/test_facade_gpu.py -m gpu -q -x > $O/pytest_a.log 2>&1; echo "exit $?" >> $O/pytest_a.log
 tail -n 3 $O/pytest_a.log
 stamp "scene B throughput"
-timeout 300 python tools/bench_scene_b.py 1024 100 > $O/scene_b_1024.log 2>&1; cat $O/scene_b_1024.log
+GE_VERBOSE=1 timeout 300 python tools/bench_scene_b.py 1024 100 > $O/scene_b_1024.log 2>&1; cat $O/scene_b_1024.log; GE_MAXCON=96 GE_VERBOSE=1 timeout 300 python tools/bench_scene_b.py 1024 100 > $O/scene_b_1024_mc96.log 2>&1; tail -3 $O/scene_b_1024_mc96.log
 timeout 300 python tools/bench_scene_b.py 2048 100 > $O/scene_b_2048.log 2>&1; tail -1 $O/scene_b_2048.log
 timeout 300 python tools/bench_scene_b.py 4096 50 > $O/scene_b_4096.log 2>&1; tail -1 $O/scene_b_4096.log
 stamp "sanitizer on the CTA build (memcheck + synccheck + racecheck has no shared workspace to look at)"
