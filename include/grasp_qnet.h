@@ -9,6 +9,7 @@
  */
 #ifndef GRASP_QNET_H
 #define GRASP_QNET_H
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -63,6 +64,39 @@ int gq_obs_to_state_train(const unsigned char* rgb, const float* depth, float de
                           void* state_nhwc_bf16, int B, int HW, void* stream);
 /* output.view(-1).max(0) per image (Grasping_Agent_multidiscrete.py:295-299): q [B,n] -> idx [B] int32 (rot*HW + y*W + x), val [B] f32 */
 int gq_argmax(const float* q, int B, int n, int* idx, float* val, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------------------------
+ * Learner: the compute of Grasp_Agent.learn() (Grasping_Agent_multidiscrete.py:388-446, optimiser :153-156) - see csrc/qnet_learn.cuh.
+ * All buffers [dev]; activations NHWC bf16, pre-BatchNorm outputs fp32, gradients of activations bf16, of parameters fp32. */
+/* BatchNorm over the whole batch (learn() forwards B images at once, training mode): per-image sums -> batch sums, in place.
+ * stats [B,C,2] as written by gq_conv_tc. */
+int gq_bn_batch_merge(float* stats, int B, int C, void* stream);
+/* q_pred = net(state).view(B,-1).gather(1, action); loss = binary_cross_entropy(q_pred, reward) (Grasping_Agent_multidiscrete.py:426-443)
+ * + backward through sigmoid, the bilinear 2x up-sampling of the head planes and the 1x1 head convolution (Modules.py:250-251,281-283):
+ * q [B,A,2H,2W] f32 (forward output), x [B,H,W,64] bf16 (head input), w_head [A,64] f32, action [B] int64 (rot*4HW + y*2W + x), reward [B] f32.
+ * Out: loss_terms [B] (mean = the loss), qsel [B] = q_pred, dX [B,H,W,64] bf16, dW_head [A,64], db_head [A]; partials [B,A,64], [B,A]. */
+int gq_loss_head_bwd(const float* q, const void* x, const float* w_head, const long long* action, const float* reward, int B, int A, int H, int W,
+                     float* loss_terms, float* qsel, void* dX, float* dW_partial, float* db_partial, float* dW_head, float* db_head, void* stream);
+/* backward of y = relu(BatchNorm(o) [+ identity]) with batch statistics (BasicBlock, Modules.py:128-142): dY, act = y [B,HW,C] bf16, o [B,HW,C] f32,
+ * stats merged [B,C,2], gamma [C].  Out: d_o [B,HW,C] bf16 (gradient w.r.t. the convolution output), dgamma, dbeta [C] (either may be NULL),
+ * dpre_out (NULL or [B,HW,C] bf16) = dY * (y > 0), the gradient that also enters the identity branch.
+ * scratch_part: ceil(B*HW/128) * C * 2 floats, scratch_sums: 2 C floats. */
+int gq_bn_relu_bwd(const void* dY, const void* act, const float* o, const float* stats, const float* gamma, int B, int HW, int C, float eps,
+                   void* dpre_out, float* scratch_part, float* scratch_sums, float* dgamma, float* dbeta, void* d_o, void* stream);
+/* weight gradient of conv3x3 / conv1x1 (Modules.py:145-156): dY [B,H,W,Cout] bf16, x [B,H,W,Cin] bf16 -> dW [Cout][ks*ks][Cin] f32;
+ * scratch_part: B * Cout * ks*ks * Cin floats (split-K over the images, reduced in image order) */
+int gq_conv_wgrad(const void* dY, const void* x, float* scratch_part, float* dW, int B, int H, int W, int Cin, int Cout, int ks, void* stream);
+/* weight gradient of Perception_Module.C1 (4 -> 64, Modules.py:163): dY [B,H,W,64] bf16, x [B,4,H,W] f32 -> dW [64][3][3][4] f32;
+ * scratch_part: ceil(B*H*W/2048) * 64 * 36 floats */
+int gq_conv_first_wgrad(const void* dY, const float* x, float* scratch_part, float* dW, int B, int H, int W, void* stream);
+/* MaxPool2d(3, 2, 1) backward: x [B,H,W,C] bf16 (pool input), dY [B,ceil(H/2),ceil(W/2),C] bf16 -> dX [B,H,W,C] bf16 */
+int gq_maxpool_bwd(const void* x, const void* dY, void* dX, int B, int H, int W, int C, void* stream);
+/* UpsamplingBilinear2d(2) backward: dY [B,2H,2W,C] bf16 -> dX [B,H,W,C] bf16 */
+int gq_upsample2x_bwd(const void* dY, void* dX, int B, int H, int W, int C, void* stream);
+/* out (bf16) = a (f32) + b (f32, may be NULL) or a + c_bf16 (bf16, may be NULL): sums two gradient branches */
+int gq_add_to_bf16(const float* a, const float* b, const void* c_bf16, void* out, size_t n, void* stream);
+/* torch.optim.Adam step with weight_decay as L2 (Grasping_Agent_multidiscrete.py:153-156): p, g, m, v [n] f32, step counted from 1 */
+int gq_adam(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
 
 #ifdef __cplusplus
 }

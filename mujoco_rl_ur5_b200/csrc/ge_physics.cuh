@@ -854,18 +854,27 @@ __device__ __noinline__ int stage_collision(double* ws, int* wi, int lane, int* 
     }
     gsync();
     int nslots = ncon + k < L.maxcon ? ncon + k : L.maxcon;
-    // stable in-place compaction by warp 0: record j moves down to the next free slot (never overtakes an unread record)
-    int out = ncon;
-    for (int j = ncon; j < nslots; j++) {
-      int p = cpair[j];
-      if (p < 0) continue;
-      if (out != j && wid == 0) {
-        for (int q = wl; q < C_FRAME + 3; q += 32) con[out * L.cstride + q] = con[j * L.cstride + q];
-        if (wl == 0) cpair[out] = p;
+    // every thread counts the hits first (read-only), THEN warp 0 alone compacts in place: record j moves down to the next free slot
+    // (never overtakes an unread record).  (r02d: a version in which all threads walked the flags while warp 0 was already moving
+    // records let a slow thread read a flag that had just been overwritten - its contact count then differed from the others';
+    // found by racecheck once the workspace was in shared memory.)
+    int nhit = 0;
+    for (int j = ncon; j < nslots; j++) nhit += cpair[j] >= 0;
+    gsync();
+    if (wid == 0) {
+      int o2 = ncon;
+      for (int j = ncon; j < nslots; j++) {
+        const int p = cpair[j];
+        __syncwarp();  // every lane has read flag j before lane 0 may overwrite a lower slot
+        if (p < 0) continue;
+        if (o2 != j) {
+          for (int q = wl; q < C_FRAME + 3; q += 32) con[o2 * L.cstride + q] = con[j * L.cstride + q];
+          if (wl == 0) cpair[o2] = p;
+        }
+        o2++;
       }
-      out++;
-      gsync();
     }
+    const int out = ncon + nhit;
     if (overflow) *status |= 1;
     ncon = out;
     gsync();

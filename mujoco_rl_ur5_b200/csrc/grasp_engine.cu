@@ -519,7 +519,9 @@ extern "C" int ge_create(const void* model_blob, size_t nbytes, int n_envs, int 
   // CTA-per-env build: the workspace of ONE env per CTA in shared memory.  The Hessian block region is capped so that two CTAs share
   // an SM (2 x 113 KB); a Hessian build that needs more (one huge island) uses the env's overflow row in HBM for that build.
   {
-    int maxcon = maxcon_default;
+    // 112 contacts instead of the 128 of the r01 HBM layout: with 128 the phase-aliased workspace of the 40-object scene is 116.9 KB even
+    // with an empty Hessian region - 3.3 KB over what lets two CTAs share an SM (settled piles hold 40-50 contacts; overflow is flagged)
+    int maxcon = maxcon_default > 112 ? 112 : maxcon_default;
     if (const char* ev = getenv("GE_MAXCON")) { int v = atoi(ev); if (v >= 16 && v <= 512) maxcon = v; }
     int diag = 0;
     for (int t = 0; t < m.ntree; t++) diag += tdn[t] * (tdn[t] + 1) / 2;

@@ -1080,3 +1080,4 @@ extern "C" int gq_argmax(const float* q, int B, int n, int* idx, float* val, voi
   QCK(cudaGetLastError());
   return 0;
 }
+#include "qnet_learn.cuh"

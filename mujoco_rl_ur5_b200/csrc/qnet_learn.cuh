@@ -1,0 +1,393 @@
+// Backward pass + optimiser of the pixel-wise grasp Q-network: the compute of Grasp_Agent.learn()
+// (reference: Grasping_Agent_multidiscrete.py:388-446; optimiser :153-156 Adam(lr, weight_decay 2e-5); network Modules.py:92-311).
+//
+//   q_pred = policy_net(state_batch).view(B, -1).gather(1, action_batch);  loss = binary_cross_entropy(q_pred, reward);  loss.backward();
+//   optimizer.step()
+//
+// In learn() the network sees the whole batch, so BatchNorm (training mode) normalises over batch AND pixels - unlike the acting
+// forward, which runs one image at a time (per-image statistics).  gq_bn_batch_merge turns the per-image sums the convolution
+// epilogue produces into batch sums, after which the forward kernels of qnet.cu compute exactly that.
+//
+// Data layout as in the forward: activations NHWC bf16, pre-BatchNorm convolution outputs fp32, weights [Cout][kh][kw][Cin].
+// Gradients of activations travel as bf16 between layers (fp32 inside a kernel), weight gradients and the optimiser state are fp32.
+//   dgrad (gradient w.r.t. the convolution input) = the forward tcgen05 convolution applied to dY with the spatially flipped,
+//          in/out-transposed weights (gq_conv_tc called by the host wrapper);
+//   wgrad (gradient w.r.t. the weights)           = k_wgrad below, a shared-memory tiled outer-product kernel on the CUDA cores with
+//          split-K over the images of the batch (partials reduced in image order: deterministic);
+//   everything else is element-wise / reduction glue.
+// Included at the end of qnet.cu (same library, C-ABI in include/grasp_qnet.h).
+#pragma once
+
+// ------------------------------------------------------------------------------------------------ BatchNorm over the batch
+// stats [B,C,2] per-image (sum, sum of squares) -> every image's entry := batch total / B, so that the per-image formulas
+// mean = s1 / HW, var = s2 / HW - mean^2 of k_bn_act / k_bn_scale_shift yield the statistics over B * HW values
+__global__ void k_bn_batch_merge(float* __restrict__ stats, int B, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0, s2 = 0;
+  for (int b = 0; b < B; b++) { s1 += stats[((size_t)b * C + c) * 2]; s2 += stats[((size_t)b * C + c) * 2 + 1]; }
+  const float m1 = (float)(s1 / B), m2 = (float)(s2 / B);
+  for (int b = 0; b < B; b++) { stats[((size_t)b * C + c) * 2] = m1; stats[((size_t)b * C + c) * 2 + 1] = m2; }
+}
+
+// ------------------------------------------------------------------------------------------------ loss + head backward
+// One CTA per image.  q [B,A,2H,2W] (sigmoid of the bilinearly up-sampled head output), x [B,H,W,64] bf16 (input of the head),
+// action [B] = rot * (2H*2W) + y * 2W + x, reward [B].  With v = pre-sigmoid value at the chosen pixel: dL/dv = (q - r) / B.
+// v = UP2(z)[rot, y, x] = sum of 4 bilinear taps of z = W_head x + b on the H x W map, so the gradient reaches 4 (or fewer) pixels:
+//   dx[pix,:] += g w W_head[rot,:],  dW_head[rot,:] += g w x[pix,:],  db_head[rot] += g w.
+// Outputs: loss_terms [B] (-(r log q + (1-r) log(1-q)), logs clamped at -100 like torch), dX [B,H,W,64] bf16 (zero-filled by the
+// caller, 4 rows written here), dWp [B,A,64] / dbp [B,A] per-image partials (zero except row rot), qsel [B] the gathered q.
+__global__ void __launch_bounds__(64) k_loss_head_bwd(const float* __restrict__ q, const bf16* __restrict__ x, const float* __restrict__ w_head,
+                                                     const long long* __restrict__ action, const float* __restrict__ reward, int B, int A, int H, int W,
+                                                     float* __restrict__ loss_terms, float* __restrict__ qsel, bf16* __restrict__ dX, float* __restrict__ dWp,
+                                                     float* __restrict__ dbp) {
+  const int b = blockIdx.x, c = threadIdx.x;  // thread = head input channel
+  const int OH = 2 * H, OW = 2 * W;
+  const long long a = action[b];
+  const int rot = (int)(a / ((long long)OH * OW)), oy = (int)((a / OW) % OH), ox = (int)(a % OW);
+  const float qv = q[(((size_t)b * A + rot) * OH + oy) * OW + ox], r = reward[b];
+  if (c == 0) {
+    loss_terms[b] = -(r * fmaxf(logf(qv), -100.f) + (1.f - r) * fmaxf(logf(1.f - qv), -100.f));
+    qsel[b] = qv;
+  }
+  const float g = (qv - r) / (float)B;
+  const float fy = oy * (float)(H - 1) / (float)(OH - 1), fx = ox * (float)(W - 1) / (float)(OW - 1);
+  const int y0 = (int)fy, x0 = (int)fx, y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float wy = fy - y0, wx = fx - x0;
+  const int py[4] = {y0, y0, y1, y1}, px[4] = {x0, x1, x0, x1};
+  const float wt[4] = {(1 - wx) * (1 - wy), wx * (1 - wy), (1 - wx) * wy, wx * wy};
+  for (int aa = 0; aa < A; aa++) dWp[((size_t)b * A + aa) * 64 + c] = 0.f;
+  if (c < A) dbp[(size_t)b * A + c] = 0.f;
+  __syncthreads();
+  const float wh = w_head[rot * 64 + c];
+  float dw = 0.f, db = 0.f;
+  // coincident taps (image border) are merged first so that a pixel row is written once
+  float acc[4] = {wt[0], wt[1], wt[2], wt[3]};
+  bool live[4] = {true, true, true, true};
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < i; j++)
+      if (live[i] && live[j] && py[i] == py[j] && px[i] == px[j]) { acc[j] += acc[i]; live[i] = false; }
+  for (int i = 0; i < 4; i++) {
+    if (!live[i]) continue;
+    const size_t pix = ((size_t)b * H + py[i]) * W + px[i];
+    const float xv = __bfloat162float(x[pix * 64 + c]);
+    dw += g * acc[i] * xv;
+    db += g * acc[i];
+    dX[pix * 64 + c] = __float2bfloat16(g * acc[i] * wh);
+  }
+  dWp[((size_t)b * A + rot) * 64 + c] = dw;
+  if (c == 0) dbp[(size_t)b * A + rot] = db;
+}
+
+// out[n] = sum over rows r < R of part[r][n], in row order (deterministic); used for per-image partials and split-K partials
+__global__ void k_reduce_rows(const float* __restrict__ part, float* __restrict__ out, int R, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int r = 0; r < R; r++) s += part[(size_t)r * n + i];
+  out[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------ BatchNorm (+ReLU) backward
+// Layer: y = relu(gamma * xhat + beta [+ identity]),  xhat = (o - mean) * rstd with batch statistics (from the merged stats).
+// dY [B*HW, C] bf16 gradient w.r.t. y, act [B*HW, C] bf16 = y (ReLU mask: y > 0), o [B*HW, C] fp32 pre-BN convolution output.
+// Pass 1 (k_bn_bwd_reduce): per CTA (a block of rows) and channel: sum dpre, sum dpre * xhat, with dpre = dY * (y > 0); optionally
+//         writes dpre as bf16 (the gradient that also flows into the shortcut convolution / the identity branch).
+// Pass 2 (k_bn_bwd_apply):  d_o = gamma * rstd * (dpre - S1 / N - xhat * S2 / N) as bf16;  dgamma = S2, dbeta = S1.
+__global__ void __launch_bounds__(256) k_bn_bwd_reduce(const bf16* __restrict__ dY, const bf16* __restrict__ act, const float* __restrict__ o,
+                                                       const float* __restrict__ stats, int rows, int C, int HW, float eps, int rows_per_cta,
+                                                       bf16* __restrict__ dpre_out, float* __restrict__ part) {
+  // thread t handles channels t, t + 256, ...; consecutive threads read consecutive channels of a row (coalesced)
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float s1 = stats[(size_t)c * 2], s2 = stats[(size_t)c * 2 + 1];  // image 0's entry = batch value after the merge
+    const float mean = s1 / HW, var = fmaxf(s2 / HW - mean * mean, 0.f), rstd = rsqrtf(var + eps);
+    float a1 = 0.f, a2 = 0.f;
+    for (int r = r0; r < r1; r++) {
+      const size_t i = (size_t)r * C + c;
+      const float d = __bfloat162float(act[i]) > 0.f ? __bfloat162float(dY[i]) : 0.f;
+      if (dpre_out) dpre_out[i] = __float2bfloat16(d);
+      a1 += d;
+      a2 += d * ((o[i] - mean) * rstd);
+    }
+    part[((size_t)blockIdx.x * C + c) * 2] = a1;
+    part[((size_t)blockIdx.x * C + c) * 2 + 1] = a2;
+  }
+}
+// sums[C,2] = per-channel totals of the partials in CTA order; dgamma[c] = sums[c][1], dbeta[c] = sums[c][0]
+__global__ void k_bn_bwd_sums(const float* __restrict__ part, int nparts, int C, float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a1 = 0, a2 = 0;
+  for (int k = 0; k < nparts; k++) { a1 += part[((size_t)k * C + c) * 2]; a2 += part[((size_t)k * C + c) * 2 + 1]; }
+  sums[c * 2] = (float)a1; sums[c * 2 + 1] = (float)a2;
+  if (dgamma) dgamma[c] = (float)a2;
+  if (dbeta) dbeta[c] = (float)a1;
+}
+__global__ void __launch_bounds__(256) k_bn_bwd_apply(const bf16* __restrict__ dY, const bf16* __restrict__ act, const float* __restrict__ o,
+                                                      const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ sums,
+                                                      size_t n, int C, int HW, float invN, float eps, bf16* __restrict__ d_o) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = (int)(i % C);
+  const float s1 = stats[(size_t)c * 2], s2 = stats[(size_t)c * 2 + 1];
+  const float mean = s1 / HW, var = fmaxf(s2 / HW - mean * mean, 0.f), rstd = rsqrtf(var + eps);
+  const float xhat = (o[i] - mean) * rstd;
+  const float d = __bfloat162float(act[i]) > 0.f ? __bfloat162float(dY[i]) : 0.f;
+  d_o[i] = __float2bfloat16(gamma[c] * rstd * (d - sums[c * 2] * invN - xhat * sums[c * 2 + 1] * invN));
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradient of a convolution
+// dW[co][tap][ci] = sum over images b and pixels p of dY[b,p,co] * X[b, p + tap, ci]  (zero outside the image).
+// grid (Cout / 64, Cin / 64, taps * B): one CTA = a 64 x 64 tile of (co, ci) for one tap and ONE image (split-K over the batch; the
+// partials [B][Cout][taps][Cin] are summed in image order by k_reduce_rows).  256 threads, each a 4 x 4 register tile; the K loop runs
+// over the pixels in chunks of 32 rows staged through shared memory (rows of dY / X are channel-contiguous: coalesced 128-byte reads).
+#define WG_T 64
+#define WG_K 32
+__global__ void __launch_bounds__(256) k_wgrad(const bf16* __restrict__ dY, const bf16* __restrict__ X, float* __restrict__ part, int H, int W, int Cin, int Cout,
+                                               int ks) {
+  __shared__ float sA[WG_K][WG_T + 4];  // dY chunk [pixel][co]
+  __shared__ float sB[WG_K][WG_T + 4];  // X chunk  [pixel][ci]
+  const int taps = ks * ks, pad = ks / 2;
+  const int co0 = blockIdx.x * WG_T, ci0 = blockIdx.y * WG_T, tap = blockIdx.z % taps, b = blockIdx.z / taps;
+  const int dh = tap / ks - pad, dw = tap % ks - pad, HW = H * W;
+  const int tid = threadIdx.x, tm = (tid / 16) * 4, tn = (tid % 16) * 4;  // 16 x 16 threads, 4 x 4 outputs each
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+  const bf16* dYb = dY + (size_t)b * HW * Cout;
+  const bf16* Xb = X + (size_t)b * HW * Cin;
+  const int lr = tid / 8, lc = (tid % 8) * 8;  // loader: row lr of the chunk, 8 consecutive channels starting at lc
+  for (int p0 = 0; p0 < HW; p0 += WG_K) {
+    {
+      const int p = p0 + lr;
+      float va[8], vb[8];
+      const bool okp = p < HW;
+      const int oh = okp ? p / W : 0, ow = okp ? p - oh * W : 0, ih = oh + dh, iw = ow + dw;
+      const bool okx = okp && ih >= 0 && ih < H && iw >= 0 && iw < W;
+      if (okp) {
+        const uint4 qa = *(const uint4*)(dYb + (size_t)p * Cout + co0 + lc);
+        const __nv_bfloat162* pa = (const __nv_bfloat162*)&qa;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const float2 f = __bfloat1622float2(pa[k]); va[2 * k] = f.x; va[2 * k + 1] = f.y; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) va[k] = 0.f;
+      }
+      if (okx) {
+        const uint4 qb = *(const uint4*)(Xb + ((size_t)ih * W + iw) * Cin + ci0 + lc);
+        const __nv_bfloat162* pb = (const __nv_bfloat162*)&qb;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const float2 f = __bfloat1622float2(pb[k]); vb[2 * k] = f.x; vb[2 * k + 1] = f.y; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) vb[k] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) { sA[lr][lc + k] = va[k]; sB[lr][lc + k] = vb[k]; }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < WG_K; k++) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) { a[i] = sA[k][tm + i]; bb[i] = sB[k][tn + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] += a[i] * bb[j];
+    }
+    __syncthreads();
+  }
+  float* out = part + (size_t)b * Cout * taps * Cin;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) out[((size_t)(co0 + tm + i) * taps + tap) * Cin + ci0 + tn + j] = acc[i][j];
+}
+
+// first convolution (4 -> 64 channels, 3x3, no bias; Modules.py:163): dW[co][tap][c] = sum_{b,p} dY[b,p,co] * x[b,c,p+tap] with x the
+// network input [B,4,H,W] f32.  grid (36, chunks): CTA (j, k) reduces pixel chunk k for the 36 (tap, c) pairs -> part [chunks][64][36].
+__global__ void __launch_bounds__(64) k_conv_first_wgrad(const bf16* __restrict__ dY, const float* __restrict__ x, float* __restrict__ part, int B, int H, int W,
+                                                         int pix_per_cta) {
+  const int j = blockIdx.x, tap = j / 4, c = j % 4, co = threadIdx.x, HW = H * W;
+  const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+  const size_t n = (size_t)B * HW, i0 = (size_t)blockIdx.y * pix_per_cta, i1 = i0 + pix_per_cta < n ? i0 + pix_per_cta : n;
+  float acc = 0.f;
+  for (size_t i = i0; i < i1; i++) {
+    const int b = (int)(i / HW), p = (int)(i % HW), oh = p / W, ow = p % W, ih = oh + dh, iw = ow + dw;
+    if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+    acc += __bfloat162float(dY[i * 64 + co]) * x[((size_t)(b * 4 + c) * H + ih) * W + iw];
+  }
+  part[((size_t)blockIdx.y * 64 + co) * 36 + j] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------ pooling / up-sampling backward, glue
+// MaxPool2d(3, stride 2, padding 1) backward in gather form: input pixel (ih, iw) receives dY of every window whose arg-max it is
+// (first maximum in window scan order, as PyTorch does).  x [B,H,W,C] bf16 (the pool's input), dY [B,OH,OW,C] bf16 -> dX [B,H,W,C] bf16
+__global__ void k_maxpool_bwd(const bf16* __restrict__ x, const bf16* __restrict__ dY, bf16* __restrict__ dX, int B, int H, int W, int C) {
+  const int OH = (H + 1) / 2, OW = (W + 1) / 2;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)B * H * W * C;
+  if (i >= n) return;
+  const int c = (int)(i % C), iw = (int)((i / C) % W), ih = (int)((i / ((size_t)C * W)) % H), b = (int)(i / ((size_t)C * W * H));
+  float g = 0.f;
+  // windows (oh, ow) that contain (ih, iw): oh*2-1 <= ih <= oh*2+1
+  for (int oh = (ih) / 2; oh <= (ih + 1) / 2 && oh < OH; oh++)
+    for (int ow = (iw) / 2; ow <= (iw + 1) / 2 && ow < OW; ow++) {
+      // arg-max of the window
+      float best = -3.0e38f; int bh = -1, bw = -1;
+      for (int kh = 0; kh < 3; kh++)
+        for (int kw = 0; kw < 3; kw++) {
+          const int hh = oh * 2 - 1 + kh, ww = ow * 2 - 1 + kw;
+          if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+          const float v = __bfloat162float(x[(((size_t)b * H + hh) * W + ww) * C + c]);
+          if (v > best) { best = v; bh = hh; bw = ww; }
+        }
+      if (bh == ih && bw == iw) g += __bfloat162float(dY[(((size_t)b * OH + oh) * OW + ow) * C + c]);
+    }
+  dX[i] = __float2bfloat16(g);
+}
+// UpsamplingBilinear2d(scale 2, align_corners=True) backward in gather form: input pixel (ih, iw) collects w * dY from the output pixels
+// whose 2x2 footprint contains it.  dY [B,2H,2W,C] bf16 -> dX [B,H,W,C] bf16
+__global__ void k_upsample_bwd(const bf16* __restrict__ dY, bf16* __restrict__ dX, int B, int H, int W, int C) {
+  const int OH = 2 * H, OW = 2 * W;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)B * H * W * C;
+  if (i >= n) return;
+  const int c = (int)(i % C), iw = (int)((i / C) % W), ih = (int)((i / ((size_t)C * W)) % H), b = (int)(i / ((size_t)C * W * H));
+  const float ry = (float)(H - 1) / (float)(OH - 1), rx = (float)(W - 1) / (float)(OW - 1);
+  // output rows whose source coordinate fy = oy * ry lies in (ih - 1, ih + 1): oy in (ih-1)/ry .. (ih+1)/ry
+  const int oy_lo = max(0, (int)floorf((ih - 1) / ry)), oy_hi = min(OH - 1, (int)ceilf((ih + 1) / ry));
+  const int ox_lo = max(0, (int)floorf((iw - 1) / rx)), ox_hi = min(OW - 1, (int)ceilf((iw + 1) / rx));
+  float g = 0.f;
+  for (int oy = oy_lo; oy <= oy_hi; oy++) {
+    const float fy = oy * ry;
+    const int y0 = (int)fy, y1 = min(y0 + 1, H - 1);
+    const float wy = fy - y0;
+    float cy = 0.f;
+    if (y0 == ih) cy += 1.f - wy;
+    if (y1 == ih) cy += wy;
+    if (cy == 0.f) continue;
+    for (int ox = ox_lo; ox <= ox_hi; ox++) {
+      const float fx = ox * rx;
+      const int x0 = (int)fx, x1 = min(x0 + 1, W - 1);
+      const float wx = fx - x0;
+      float cx = 0.f;
+      if (x0 == iw) cx += 1.f - wx;
+      if (x1 == iw) cx += wx;
+      if (cx == 0.f) continue;
+      g += cy * cx * __bfloat162float(dY[(((size_t)b * OH + oy) * OW + ox) * C + c]);
+    }
+  }
+  dX[i] = __float2bfloat16(g);
+}
+// out = bf16(a + b) (b may be null): sum of the gradients of two branches / fp32 dgrad output -> bf16 activation gradient
+__global__ void k_add_to_bf16(const float* __restrict__ a, const float* __restrict__ b, bf16* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = __float2bfloat16(a[i] + (b ? b[i] : 0.f));
+}
+// out = bf16(a + float(c)) with c bf16 (adds a bf16 gradient branch to an fp32 one)
+__global__ void k_add_bf16_to_bf16(const float* __restrict__ a, const bf16* __restrict__ c, bf16* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = __float2bfloat16(a[i] + __bfloat162float(c[i]));
+}
+
+// ------------------------------------------------------------------------------------------------ Adam (torch.optim.Adam, weight_decay = L2 added to the gradient)
+// p, g, m, v fp32 [n];  step t (1-based):  g' = g + wd p;  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;
+// p -= lr * (m / (1 - b1^t)) / (sqrt(v / (1 - b2^t)) + eps)          (Grasping_Agent_multidiscrete.py:153-156: lr, wd = 2e-5, defaults otherwise)
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n, float lr, float b1, float b2,
+                       float eps, float wd, float bc1, float bc2) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gg = g[i] + wd * p[i];
+  const float mm = b1 * m[i] + (1.f - b1) * gg, vv = b2 * v[i] + (1.f - b2) * gg * gg;
+  m[i] = mm; v[i] = vv;
+  p[i] -= lr * (mm / bc1) / (sqrtf(vv / bc2) + eps);
+}
+
+// ------------------------------------------------------------------------------------------------ C-ABI
+extern "C" int gq_bn_batch_merge(float* stats, int B, int C, void* stream) {
+  if (!stats || B <= 0 || C <= 0) { snprintf(q_err, sizeof q_err, "gq_bn_batch_merge: bad argument"); return -1; }
+  k_bn_batch_merge<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, B, C);
+  QCK(cudaGetLastError());
+  return 0;
+}
+extern "C" int gq_loss_head_bwd(const float* q, const void* x, const float* w_head, const long long* action, const float* reward, int B, int A, int H, int W,
+                                float* loss_terms, float* qsel, void* dX, float* dW_partial, float* db_partial, float* dW_head, float* db_head, void* stream) {
+  if (!q || !x || !w_head || !action || !reward || !loss_terms || !qsel || !dX || !dW_partial || !db_partial || !dW_head || !db_head || A > 64) {
+    snprintf(q_err, sizeof q_err, "gq_loss_head_bwd: bad argument");
+    return -1;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  QCK(cudaMemsetAsync(dX, 0, (size_t)B * H * W * 64 * sizeof(bf16), st));
+  k_loss_head_bwd<<<B, 64, 0, st>>>(q, (const bf16*)x, w_head, action, reward, B, A, H, W, loss_terms, qsel, (bf16*)dX, dW_partial, db_partial);
+  k_reduce_rows<<<(A * 64 + 127) / 128, 128, 0, st>>>(dW_partial, dW_head, B, (size_t)A * 64);
+  k_reduce_rows<<<1, 128, 0, st>>>(db_partial, db_head, B, (size_t)A);
+  QCK(cudaGetLastError());
+  return 0;
+}
+extern "C" int gq_bn_relu_bwd(const void* dY, const void* act, const float* o, const float* stats, const float* gamma, int B, int HW, int C, float eps,
+                              void* dpre_out, float* scratch_part, float* scratch_sums, float* dgamma, float* dbeta, void* d_o, void* stream) {
+  if (!dY || !act || !o || !stats || !gamma || !scratch_part || !scratch_sums || !d_o) { snprintf(q_err, sizeof q_err, "gq_bn_relu_bwd: bad argument"); return -1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows = B * HW, rpc = 128, nparts = (rows + rpc - 1) / rpc;
+  k_bn_bwd_reduce<<<nparts, 256, 0, st>>>((const bf16*)dY, (const bf16*)act, o, stats, rows, C, HW, eps, rpc, (bf16*)dpre_out, scratch_part);
+  k_bn_bwd_sums<<<(C + 127) / 128, 128, 0, st>>>(scratch_part, nparts, C, scratch_sums, dgamma, dbeta);
+  const size_t n = (size_t)rows * C;
+  k_bn_bwd_apply<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const bf16*)dY, (const bf16*)act, o, stats, gamma, scratch_sums, n, C, HW, 1.f / (float)rows, eps,
+                                                                (bf16*)d_o);
+  QCK(cudaGetLastError());
+  return 0;
+}
+// scratch_part of gq_bn_relu_bwd: ceil(B*HW / 128) * C * 2 floats
+extern "C" int gq_conv_wgrad(const void* dY, const void* x, float* scratch_part, float* dW, int B, int H, int W, int Cin, int Cout, int ks, void* stream) {
+  if (!dY || !x || !scratch_part || !dW || (ks != 1 && ks != 3) || Cin % 64 || Cout % 64) { snprintf(q_err, sizeof q_err, "gq_conv_wgrad: bad argument"); return -1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int taps = ks * ks;
+  dim3 grid(Cout / WG_T, Cin / WG_T, taps * B);
+  k_wgrad<<<grid, 256, 0, st>>>((const bf16*)dY, (const bf16*)x, scratch_part, H, W, Cin, Cout, ks);
+  const size_t n = (size_t)Cout * taps * Cin;
+  k_reduce_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scratch_part, dW, B, n);
+  QCK(cudaGetLastError());
+  return 0;
+}
+extern "C" int gq_conv_first_wgrad(const void* dY, const float* x, float* scratch_part, float* dW, int B, int H, int W, void* stream) {
+  if (!dY || !x || !scratch_part || !dW) { snprintf(q_err, sizeof q_err, "gq_conv_first_wgrad: bad argument"); return -1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)B * H * W;
+  const int ppc = 2048, chunks = (int)((n + ppc - 1) / ppc);
+  k_conv_first_wgrad<<<dim3(36, chunks), 64, 0, st>>>((const bf16*)dY, x, scratch_part, B, H, W, ppc);
+  k_reduce_rows<<<(64 * 36 + 127) / 128, 128, 0, st>>>(scratch_part, dW, chunks, (size_t)64 * 36);
+  QCK(cudaGetLastError());
+  return 0;
+}
+extern "C" int gq_maxpool_bwd(const void* x, const void* dY, void* dX, int B, int H, int W, int C, void* stream) {
+  const size_t n = (size_t)B * H * W * C;
+  k_maxpool_bwd<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)dY, (bf16*)dX, B, H, W, C);
+  QCK(cudaGetLastError());
+  return 0;
+}
+extern "C" int gq_upsample2x_bwd(const void* dY, void* dX, int B, int H, int W, int C, void* stream) {
+  const size_t n = (size_t)B * H * W * C;
+  k_upsample_bwd<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dY, (bf16*)dX, B, H, W, C);
+  QCK(cudaGetLastError());
+  return 0;
+}
+extern "C" int gq_add_to_bf16(const float* a, const float* b, const void* c_bf16, void* out, size_t n, void* stream) {
+  if (!a || !out || (b && c_bf16)) { snprintf(q_err, sizeof q_err, "gq_add_to_bf16: bad argument"); return -1; }
+  if (c_bf16) k_add_bf16_to_bf16<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, (const bf16*)c_bf16, (bf16*)out, n);
+  else k_add_to_bf16<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, b, (bf16*)out, n);
+  QCK(cudaGetLastError());
+  return 0;
+}
+extern "C" int gq_adam(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                       void* stream) {
+  if (!p || !g || !m || !v || step < 1) { snprintf(q_err, sizeof q_err, "gq_adam: bad argument"); return -1; }
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  k_adam<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2);
+  QCK(cudaGetLastError());
+  return 0;
+}
