@@ -50,7 +50,10 @@ __device__ __forceinline__ void jac_column(const double* c, int dim, const doubl
 
 // owner warp of the island a coupled tree belongs to (CTA-per-env build: islands are dealt out to the warps; their Hessian blocks
 // are disjoint, so the warps never touch the same entry)
-__device__ __forceinline__ int island_owner(const int* island, int t) { return island[t] % GE_NW; }
+// The owner is chosen per Hessian build by longest-processing-time-first over the islands' cubic cost (build_hessian) and kept in slot 1
+// of the representative's list row: with `island % GE_NW` one warp regularly held the two largest islands of a pile while the others
+// idled at the next barrier (r02f ncu: barrier = 40-47 % of the stall cycles in build_hessian / cholesky_solve).
+__device__ __forceinline__ int island_owner(const int* island, const int* tlist, int t) { return tlist[island[t] * 16 + 1]; }
 // per-tree bookkeeping of one Hessian build: block offset (of the tree's own block, or of its island's block) and, for coupled trees,
 // the tree's first row inside the island block
 #define T_HOFF(tlist, t) (tlist)[(t) * GE_TLIST + GE_TCAP]
@@ -162,7 +165,21 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
     }
     const bool ovf = tot > L.hcap;
     if (ovf) H = g_hovf;
-    if (lane == 0) wi[L.i_hflag] = ovf ? 1 : 0;
+    if (lane == 0) {
+      wi[L.i_hflag] = ovf ? 1 : 0;
+      // island -> warp: islands in descending order of size would be ideal; taking them in index order and always feeding the least
+      // loaded warp is within a small factor and needs no sort
+      long long load[GE_NW];
+      for (int w = 0; w < GE_NW; w++) load[w] = 0;
+      for (int u = 0; u < m.ntree; u++) {
+        if (!tcoupled[u] || island[u] != u) continue;
+        const long long n = tlist[u * GE_TLIST];
+        int best = 0;
+        for (int w = 1; w < GE_NW; w++) if (load[w] < load[best]) best = w;
+        load[best] += n * n * n + 64 * n * n;
+        tlist[u * GE_TLIST + 1] = best;
+      }
+    }
   }
 #endif
   gsync();
@@ -237,7 +254,7 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
     const bool c1 = t1 >= 0 && tcoupled[t1], c2 = t2 >= 0 && tcoupled[t2];
     if (!(c1 || c2)) continue;
     const int tk = c1 ? t1 : t2;
-    if (GE_NW > 1 && island_owner(island, tk) != wid) continue;
+    if (GE_NW > 1 && island_owner(island, tlist, tk) != wid) continue;
     double* Hb = H + T_HOFF(tlist, tk);
     const double* c = ws + L.con + ci * L.cstride;
     int dim = wi[L.i_cdim + ci];
@@ -271,7 +288,7 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
       int A = wi[L.i_srA + i], B = wi[L.i_srB + i];
       const int tA = m.dof_treeindex[A];
       if (!tcoupled[tA]) continue;
-      if (GE_NW > 1 && island_owner(island, tA) != wid) continue;
+      if (GE_NW > 1 && island_owner(island, tlist, tA) != wid) continue;
       double* Hb = H + T_HOFF(tlist, tA);
       double D = srv(ws, SR_D, i), ca = srv(ws, SR_CA, i), cb = srv(ws, SR_CB, i);
       const int ra = tcount[tA] + A - m.tree_dofadr[tA];
@@ -422,7 +439,7 @@ __device__ __noinline__ void cholesky_solve(double* ws, int* wi, double* x, cons
     const int n = tlist[rep * GE_TLIST];  // island size, recorded by build_hessian
     int* idx = idx_all + idx_off;
     idx_off += n;
-    if (GE_NW > 1 && island_owner(island, rep) != wid) continue;
+    if (GE_NW > 1 && island_owner(island, tlist, rep) != wid) continue;
     double* Hb = H + T_HOFF(tlist, rep);
     {
       int r0 = 0;

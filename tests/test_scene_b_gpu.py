@@ -48,8 +48,10 @@ def engine_b(scene_b):
     eng.close()
 
 
-def test_scene_b_uses_hbm_workspace(engine_b):
-    assert engine_b.size(9) == 1 and engine_b.size(1) == 248 and engine_b.size(6) >= 128
+def test_scene_b_uses_the_big_scene_build(engine_b):
+    """ge_size(9) == 1: the CTA-per-env build (r01: HBM-row workspace; r02: one env per CTA of 4 warps, workspace in shared memory)"""
+    assert engine_b.size(9) == 1 and engine_b.size(1) == 248 and engine_b.size(6) >= 96
+    assert engine_b.size(7) <= 116736 - 1024  # two CTAs (= two envs) per SM
 
 
 @pytest.mark.parametrize("settle", [0, 400])
