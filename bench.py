@@ -409,6 +409,39 @@ def run_ours(args):
         envq.close()
         del envq, sub
 
+    # ---- f2: the learner's update (Grasping_Agent_multidiscrete.py:388-446: BATCH_SIZE 12 transitions, BN in train mode over the batch,
+    # gather-BCE, Adam with weight decay); under torchrun the fp32 gradient all-reduce over the default process group is inside the step
+    linfo = None
+    if "learn" in legs:
+        from mujoco_rl_ur5_b200.qnet_learn import QNetLearner
+
+        lb = 12
+        g = torch.Generator(device="cpu").manual_seed(7 + rank)
+        st = torch.rand(lb, 4, 200, 200, generator=g).to(dev)
+        ac = torch.randint(0, 6 * 200 * 200, (lb, 1), generator=g).to(dev)
+        rw = (torch.rand(lb, 1, generator=g) < 0.3).float().to(dev)
+        import torch.distributed as dist
+
+        learner = QNetLearner(seed=0, device=local, process_group=dist.group.WORLD if world > 1 else None)
+        for _ in range(2):
+            learner.learn_step(st, ac, rw)
+        barrier()
+        l_l0 = learner.launches
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(args.qnet_reps):
+            loss_l = learner.learn_step(st, ac, rw)
+        e1.record()
+        barrier()
+        lms = e0.elapsed_time(e1) / args.qnet_reps
+        ltf = lb * 3 * 41.99424e9 / (lms * 1e-3) / 1e12  # forward + dgrad + wgrad ~ 3x the forward MACs
+        linfo = {"batch_per_gpu": lb, "ms_per_update": lms, "updates_per_s": 1e3 / lms, "transitions_per_s": world * lb * 1e3 / lms, "tflops_per_gpu": ltf,
+                 "kernels_per_update": (learner.launches - l_l0) // max(args.qnet_reps, 1), "loss": loss_l,
+                 "collective": ("all_reduce of %.1f MB fp32 gradients over %d ranks (NCCL)" % (learner.grad.numel() * 4 / 1e6, world)) if world > 1 else None,
+                 "note": "QNetLearner.learn_step: forward (tcgen05) with batch-statistics BN, gather-BCE, dgrad (tcgen05), wgrad (CUDA-core tiles), Adam; "
+                         "includes the loss .item() read like the reference"}
+        del learner, st, ac, rw
+
     configs = {}
     # ---- BASELINE config 3: 4096 envs + 200x200 RGB-D raster, fixed-size objects (scene A1 = iteration 1, README.md:20), render every
     # attempt, actions through the depth image like GraspEnv.step
@@ -535,7 +568,7 @@ def run_ours(args):
                                                      "render -> rewards AND the whole observation (rgb u8 + depth f32) copied to pinned host memory, as the reference API "
                                                      "returns it to its caller every step"},
             "gpu_launches": int(l1 - l0), "substep_kernel_launches": int(s1 - s0),
-            "clocks": clocks, "env_status_flags": {"envs_flagged": n_flag, "or": status_or}, "qnet": qinfo, "configs": configs,
+            "clocks": clocks, "env_status_flags": {"envs_flagged": n_flag, "or": status_or}, "qnet": qinfo, "learner": linfo, "configs": configs,
         }
         print(json.dumps(out))
     if world > 1:
@@ -552,7 +585,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=256, help="control-loop iterations per busy env and step")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--legs", default="3,4,5,qnet", help="extra objects: BASELINE configs 3,4,5 and the Q-net forward alone ('' = none)")
+    ap.add_argument("--legs", default="3,4,5,qnet,learn", help="extra objects: BASELINE configs 3,4,5, the Q-net forward alone, one learner update ('' = none)")
     ap.add_argument("--leg-steps", type=int, default=2, help="timed BatchedGraspEnv.step calls of the config 3 / 4 legs")
     ap.add_argument("--config4-envs", type=int, default=512, help="environments per GPU of the config 4 leg (4096 over 8 GPUs)")
     ap.add_argument("--qnet-images", type=int, default=512, help="images of the Q-net forward leg")

@@ -21,7 +21,10 @@
 // r02: the big-scene variant gives every environment a whole CTA of 4 warps.  The stage code is the same source: lane loops stride
 // by GE_LANES, `gsync()` is __syncthreads(), reductions go through shared memory, and the pieces that are inherently warp-shaped
 // (MPR on one geom pair, the 8-lane tree groups, one dense island factorisation) are dealt out to the 4 warps.
-#define GE_LANES 128
+#ifndef GE_BIG_LANES
+#define GE_BIG_LANES 128  // (-DGE_BIG_LANES=64 / 256: experiments with 2 / 8 warps per environment, tools/build_exp_libs.sh)
+#endif
+#define GE_LANES GE_BIG_LANES
 #endif
 #define GE_NW (GE_LANES / 32)
 #define GE_ERR_TOO_LARGE (-100)  // internal: variant 0 cannot hold the scene, the dispatcher then creates variant 1
