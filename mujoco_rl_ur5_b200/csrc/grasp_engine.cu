@@ -87,15 +87,16 @@ __device__ __forceinline__ unsigned long long group_bcast_u64(unsigned long long
 }
 // blockDim = (GE_LANES, envs per CTA): threadIdx.x is the lane inside the group that owns one environment (a warp; a whole CTA of
 // GE_NW warps in the big-scene build, where blockDim.y = 1)
-// Register budget.  Warp-per-env build: `__launch_bounds__(256)` alone makes ptxas settle on 128 registers (stack 1616 B); with an explicit
-// "1 CTA per SM" it takes 246 (stack 1296 B), which still fits the 2 x 128-thread CTAs the shared memory allows (-DGE_V0_FREE_REGS, an
-// experiment).  CTA-per-env build: two CTAs per SM is what the workspace allows; the bound keeps the register file from undercutting it.
+// Register budget.  Warp-per-env build: `__launch_bounds__(256)` alone makes ptxas settle on 128 registers per thread (stack 1616 B); told
+// that one 256-thread CTA per SM is enough it takes 246 (stack 1296 B), which still fits the 2 x 128-thread CTAs the shared memory allows
+// (65 536 registers per SM) - r02g: 3.93 -> 4.20 M sub-steps/s at 4096 envs (-DGE_V0_CAP_REGS restores the old budget).
+// CTA-per-env build: two CTAs per SM is what the workspace allows; the bound keeps the register file from undercutting it.
 #if GE_NW > 1
 #define GE_RUN_BOUNDS __launch_bounds__(GE_LANES, 2)
-#elif defined(GE_V0_FREE_REGS)
-#define GE_RUN_BOUNDS __launch_bounds__(256, 1)
-#else
+#elif defined(GE_V0_CAP_REGS)
 #define GE_RUN_BOUNDS __launch_bounds__(256)
+#else
+#define GE_RUN_BOUNDS __launch_bounds__(256, 1)
 #endif
 __global__ void GE_RUN_BOUNDS k_run(EnvArrays E, int n_env, int nsub, int quota, unsigned long long ticket_base, double base_x, double base_y,
                                              double base_z, int stage_sync) {

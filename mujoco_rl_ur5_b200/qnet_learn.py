@@ -199,8 +199,20 @@ class QNetLearner:
         dx_main = self._dgrad(d_o1, wT["conv1"], B, H, W, cin, cout, 3)
         return self._to_bf16(dx_main, dx_short)
 
-    def backward(self, q, saved, action, reward):
-        """-> loss (0-dim tensor), q_pred [B]; fills self.grad (every parameter gradient of the step)"""
+    # parameter groups in the order the backward pass completes them (each one contiguous in the flat buffers)
+    GROUPS = ("1.C1.", "1.RB3.", "1.RB2.", "1.RB1.", "0.RB3.", "0.RB2.", "0.RB1.", "0.C1.")
+
+    def grad_slice(self, prefix):
+        """the contiguous piece of the flat gradient buffer that holds every parameter whose name starts with `prefix`"""
+        idx = [i for i, k in enumerate(self.names) if k.startswith(prefix)]
+        assert idx and idx == list(range(idx[0], idx[-1] + 1)), prefix
+        return self.grad[int(self.offsets[idx[0]]):int(self.offsets[idx[-1] + 1])]
+
+    def backward(self, q, saved, action, reward, on_ready=None):
+        """-> loss (0-dim tensor), q_pred [B]; fills self.grad (every parameter gradient of the step).  `on_ready(prefix)` is called as
+        soon as all gradients of one parameter group (a BasicBlock, the head, the first convolution) have been enqueued - the
+        multi-GPU learner starts that group's all-reduce there, under the rest of the backward pass."""
+        ready = on_ready if on_ready is not None else (lambda prefix: None)
         t, fw = self.torch, self.fw
         B, H, W, h, w, h2, w2 = saved["dims"]
         A = fw.A
@@ -216,17 +228,24 @@ class QNetLearner:
                                          self._p(loss_terms), self._p(qsel), self._p(d_b5), self._p(dWp), self._p(dbp), self._p(dW_head), self._p(self.g["1.C1.bias"]),
                                          self._st()), "gq_loss_head_bwd")
         self.g["1.C1.weight"].copy_(dW_head.view(A, 64, 1, 1))
+        ready("1.C1.")
         sv = saved["blocks"]
         d_u0 = self._block_bwd(5, sv[5], d_b5, B)                                   # 1.RB3 @100x100
+        ready("1.RB3.")
         d_b4 = t.empty((B, h2 * w2, 128), dtype=t.bfloat16, device=self.dev)
         self._ck(self.L.gq_upsample2x_bwd(self._p(d_u0), self._p(d_b4), B, h2, w2, 128, self._st()), "gq_upsample2x_bwd")
         d = self._block_bwd(4, sv[4], d_b4, B)                                      # 1.RB2
+        ready("1.RB2.")
         d = self._block_bwd(3, sv[3], d, B)                                         # 1.RB1
+        ready("1.RB1.")
         d = self._block_bwd(2, sv[2], d, B)                                         # 0.RB3
+        ready("0.RB3.")
         d_p1 = self._block_bwd(1, sv[1], d, B)                                      # 0.RB2 @50x50
+        ready("0.RB2.")
         d_b0 = t.empty((B, h * w, 128), dtype=t.bfloat16, device=self.dev)
         self._ck(self.L.gq_maxpool_bwd(self._p(saved["b0"]), self._p(d_p1), self._p(d_b0), B, h, w, 128, self._st()), "gq_maxpool_bwd")
         d_p0 = self._block_bwd(0, sv[0], d_b0, B)                                   # 0.RB1 @100x100
+        ready("0.RB1.")
         d_x0 = t.empty((B, H * W, 64), dtype=t.bfloat16, device=self.dev)
         self._ck(self.L.gq_maxpool_bwd(self._p(saved["x0"]), self._p(d_p0), self._p(d_x0), B, H, W, 64, self._st()), "gq_maxpool_bwd")
         n = B * H * W
@@ -234,6 +253,7 @@ class QNetLearner:
         dWf = t.empty((64, 9, 4), dtype=t.float32, device=self.dev)
         self._ck(self.L.gq_conv_first_wgrad(self._p(d_x0), self._p(saved["state"]), self._p(part), self._p(dWf), B, H, W, self._st()), "gq_conv_first_wgrad")
         self.g["0.C1.weight"].copy_(dWf.view(64, 3, 3, 4).permute(0, 3, 1, 2))
+        ready("0.C1.")
         return loss_terms.mean(), qsel
 
     # ------------------------------------------------------------------ one learn() call
@@ -242,12 +262,21 @@ class QNetLearner:
         [B,1].  Returns the loss as a float (one device->host read, like the reference's `loss.item()`)."""
         t = self.torch
         q, saved = self.forward_train(state)
-        loss, _ = self.backward(q, saved, action, reward)
+        works = []
+        on_ready = None
         if self.pg is not None:
             import torch.distributed as dist
 
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)  # the learner's one collective: 29.3 MB of fp32 gradients
-            self.grad.div_(dist.get_world_size(self.pg))
+            # the learner's one collective: the 29.3 MB of fp32 gradients averaged over the ranks, issued per parameter group (8 pieces,
+            # last layers first) on NCCL's stream as soon as the group's last wgrad kernel is enqueued, so that the transfer of the
+            # 512/256-channel blocks runs under the backward pass of the layers in front of them (Grasping_Agent_multidiscrete.py has a
+            # single process; this is north_star's "gradient/batch reduction")
+            def on_ready(prefix):
+                works.append(dist.all_reduce(self.grad_slice(prefix), op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
+
+        loss, _ = self.backward(q, saved, action, reward, on_ready)
+        for w in works:
+            w.wait()  # (stream-level wait: Adam below is ordered after the last piece)
         self.step_count += 1
         self._ck(self.L.gq_adam(self._p(self.flat), self._p(self.grad), self._p(self.m), self._p(self.v), self.flat.numel(), self.lr, self.betas[0], self.betas[1],
                                 self.eps, self.wd, self.step_count, self._st()), "gq_adam")

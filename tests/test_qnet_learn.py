@@ -255,3 +255,17 @@ def test_two_learn_steps_reduce_the_loss_on_a_fixed_batch():
     L = QNetLearner(seed=0, lr=0.001)
     losses = [L.learn_step(state, action, reward) for _ in range(4)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+def test_gradient_groups_partition_the_parameters():
+    """the per-group all-reduce of the multi-GPU learner covers every parameter exactly once, each group contiguous in the flat buffer"""
+    from mujoco_rl_ur5_b200.qnet import make_torch_qnet
+    from mujoco_rl_ur5_b200.qnet_learn import QNetLearner
+
+    names = [k for k, v in make_torch_qnet(6).state_dict().items() if v.dtype.is_floating_point and "running" not in k]
+    seen = []
+    for pre in QNetLearner.GROUPS:
+        idx = [i for i, k in enumerate(names) if k.startswith(pre)]
+        assert idx and idx == list(range(idx[0], idx[-1] + 1)), pre
+        seen += idx
+    assert sorted(seen) == list(range(len(names)))

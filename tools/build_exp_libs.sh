@@ -1,6 +1,6 @@
 #!/bin/bash
 # Experimental builds of the engine library with a different number of lanes per environment in the big-scene variant
-# (ge_variant.h: GE_BIG_LANES); V0FLAGS=-DGE_V0_FREE_REGS adds the warp-per-env variant with the uncapped register budget.  Output: exp_libs/libgrasp_engine_l<lanes>.so (git-ignored; travels with gpurun); use with GE_LIB=<path>.
+# (ge_variant.h: GE_BIG_LANES); V0FLAGS=-DGE_V0_CAP_REGS builds the warp-per-env variant with the old 128-register budget.  Output: exp_libs/libgrasp_engine_l<lanes>.so (git-ignored; travels with gpurun); use with GE_LIB=<path>.
 set -e
 cd "$(dirname "$0")/.."
 CS=mujoco_rl_ur5_b200/csrc
