@@ -12,8 +12,9 @@
 // Gradients of activations travel as bf16 between layers (fp32 inside a kernel), weight gradients and the optimiser state are fp32.
 //   dgrad (gradient w.r.t. the convolution input) = the forward tcgen05 convolution applied to dY with the spatially flipped,
 //          in/out-transposed weights (gq_conv_tc called by the host wrapper);
-//   wgrad (gradient w.r.t. the weights)           = k_wgrad below, a shared-memory tiled outer-product kernel on the CUDA cores with
-//          split-K over the images of the batch (partials reduced in image order: deterministic);
+//   wgrad (gradient w.r.t. the weights)           = k_wgrad_tc below: tcgen05 GEMM with K = pixels, both operands MN-major straight from the
+//          NHWC tensors by TMA (k_wgrad, a CUDA-core tiled kernel, is its A/B partner), split-K over the images of the batch (partials
+//          reduced in image order: deterministic);
 //   everything else is element-wise / reduction glue.
 // Included at the end of qnet.cu (same library, C-ABI in include/grasp_qnet.h).
 #pragma once
@@ -209,19 +210,37 @@ __global__ void __launch_bounds__(256) k_wgrad(const bf16* __restrict__ dY, cons
 }
 
 // first convolution (4 -> 64 channels, 3x3, no bias; Modules.py:163): dW[co][tap][c] = sum_{b,p} dY[b,p,co] * x[b,c,p+tap] with x the
-// network input [B,4,H,W] f32.  grid (36, chunks): CTA (j, k) reduces pixel chunk k for the 36 (tap, c) pairs -> part [chunks][64][36].
-__global__ void __launch_bounds__(64) k_conv_first_wgrad(const bf16* __restrict__ dY, const float* __restrict__ x, float* __restrict__ part, int B, int H, int W,
-                                                         int pix_per_cta) {
-  const int j = blockIdx.x, tap = j / 4, c = j % 4, co = threadIdx.x, HW = H * W;
-  const int dh = tap / 3 - 1, dw = tap % 3 - 1;
-  const size_t n = (size_t)B * HW, i0 = (size_t)blockIdx.y * pix_per_cta, i1 = i0 + pix_per_cta < n ? i0 + pix_per_cta : n;
-  float acc = 0.f;
+// network input [B,4,H,W] f32.  One CTA = one chunk of pixels for ALL 36 (tap, c) pairs: thread (co, quarter) walks a quarter of the
+// chunk with 36 accumulators (dY read once; the 36 input values of a pixel are the same for all threads = broadcast loads), the four
+// quarters are added in fixed order -> part [chunks][64][36].  (r02h: the first version - one CTA of 64 threads per (tap, c, chunk),
+// dY read 36 times - took 3.5 ms of a 28.8 ms update.)
+__global__ void __launch_bounds__(256) k_conv_first_wgrad(const bf16* __restrict__ dY, const float* __restrict__ x, float* __restrict__ part, int B, int H, int W,
+                                                          int pix_per_cta) {
+  __shared__ float red[4][64][37];
+  const int co = threadIdx.x & 63, q = threadIdx.x >> 6, HW = H * W, quarter = pix_per_cta / 4;
+  const size_t n = (size_t)B * HW, c0 = (size_t)blockIdx.x * pix_per_cta + (size_t)q * quarter;
+  const size_t i0 = c0 < n ? c0 : n, i1 = c0 + quarter < n ? c0 + quarter : n;
+  float acc[36];
+#pragma unroll
+  for (int j = 0; j < 36; j++) acc[j] = 0.f;
   for (size_t i = i0; i < i1; i++) {
-    const int b = (int)(i / HW), p = (int)(i % HW), oh = p / W, ow = p % W, ih = oh + dh, iw = ow + dw;
-    if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
-    acc += __bfloat162float(dY[i * 64 + co]) * x[((size_t)(b * 4 + c) * H + ih) * W + iw];
+    const int b = (int)(i / HW), p = (int)(i % HW), oh = p / W, ow = p % W;
+    const float d = __bfloat162float(dY[i * 64 + co]);
+#pragma unroll
+    for (int tap = 0; tap < 9; tap++) {
+      const int ih = oh + tap / 3 - 1, iw = ow + tap % 3 - 1;
+      if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+#pragma unroll
+      for (int c = 0; c < 4; c++) acc[tap * 4 + c] += d * __ldg(x + ((size_t)(b * 4 + c) * H + ih) * W + iw);
+    }
   }
-  part[((size_t)blockIdx.y * 64 + co) * 36 + j] = acc;
+#pragma unroll
+  for (int j = 0; j < 36; j++) red[q][co][j] = acc[j];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 64 * 36; idx += 256) {
+    const int c2 = idx / 36, j = idx % 36;
+    part[((size_t)blockIdx.x * 64 + c2) * 36 + j] = ((red[0][c2][j] + red[1][c2][j]) + red[2][c2][j]) + red[3][c2][j];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ pooling / up-sampling backward, glue
@@ -342,13 +361,166 @@ extern "C" int gq_bn_relu_bwd(const void* dY, const void* act, const float* o, c
   QCK(cudaGetLastError());
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ weight gradient on tcgen05 (r02)
+// The same contraction as k_wgrad as a tensor-core GEMM:  D[co][ci] (one filter tap, one image) = sum over pixels p of dY[p][co] * X[p + tap][ci],
+// i.e. M = 128 output channels, N = BLOCK_N input channels, K = pixels.  Both operands are pixel-major in memory ([pixel][channel], NHWC), so
+// with K = pixels they are **MN-major** UMMA operands: a shared-memory tile is K rows (pixels) of 128 bytes (64 channels), 8 rows = one
+// 1024-byte swizzle atom - exactly the image a 128-byte-swizzled TMA box of [64 channels x 128 pixels] leaves.  Canonical layout
+// (cute/atom/mma_traits_sm100.hpp, Major-MN, SWIZZLE_128B):  ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in elements - the next 64 channels
+// (second box) LBO = 16 384 bytes further, the next 8 pixels SBO = 1024 bytes further; one MMA (K = 16) consumes 16 rows = 2048 bytes.
+//   A = dY: 3-D tiled map [Cout][H*W][B], box 64 x 128 x 1 - rows past the end of the image are out of bounds and read as zeros, so the
+//           last k-step of an image contributes nothing for them whatever the X load returns there;
+//   B = X : the forward's im2col-mode map (tap passed as offsets, zero fill = convolution padding): 128 consecutive output positions.
+// grid (ceil(Cout / 128), Cin / BLOCK_N, taps * B); split-K over the images like k_wgrad (partials [B][Cout][taps][Cin], summed in image
+// order by k_reduce_rows: deterministic).  Roles as in k_conv_tc_tma: warp 0 lane 0 TMA producer, warp 1 lane 0 MMA issuer, warps 2-5
+// read the accumulator (TMEM lane quarter warp % 4 = 32 output channels each) and store it.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem_addr, const CUtensorMap* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst_smem_addr), "l"((uint64_t)tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+// shared-memory matrix descriptor, MN-major, SWIZZLE_128B (see above)
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;  // leading byte offset: next 64-element atom along M / N
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: next 8 rows along K
+  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                            // layout type SWIZZLE_128B
+  return d;
+}
+#define WT_K 128                      // pixels per k-step (= the im2col map's pixels per column)
+#define WT_BOX (WT_K * 128)           // bytes of one [64 channels x 128 pixels] box
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(192) k_wgrad_tc(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
+                                                  float* __restrict__ part, int H, int W, int Cin, int Cout, int ks) {
+  constexpr int A_STAGE = 2 * WT_BOX, B_STAGE = (BLOCK_N / 64) * WT_BOX;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE;
+  uint64_t* full = (uint64_t*)(smem + STAGES * (A_STAGE + B_STAGE));
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int taps = ks * ks, pad = ks / 2, HW = H * W, nk = (HW + WT_K - 1) / WT_K;
+  const int co0 = blockIdx.x * 128, ci0 = blockIdx.y * BLOCK_N, tap = blockIdx.z % taps, b = blockIdx.z / taps;
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tacc = *tmem_slot;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kn = 0; kn < nk; kn++) {
+        const int s = kn % STAGES, round = kn / STAGES;
+        if (round > 0) mbar_wait(&empty[s], (uint32_t)(round - 1) & 1u);
+        mbar_arrive_expect_tx(&full[s], (uint32_t)(A_STAGE + B_STAGE));
+        const int p0 = kn * WT_K, oh0 = p0 / W, ow0 = p0 - oh0 * W;
+        const uint32_t a_dst = smem_u32(sA) + (uint32_t)(s * A_STAGE), b_dst = smem_u32(sB) + (uint32_t)(s * B_STAGE);
+        tma_load_3d(a_dst, &tmap_dy, co0, p0, b, &full[s]);
+        tma_load_3d(a_dst + WT_BOX, &tmap_dy, co0 + 64, p0, b, &full[s]);  // (Cout = 64: wholly out of bounds -> zeros, rows 64..127 of D unused)
+#pragma unroll
+        for (int j = 0; j < BLOCK_N / 64; j++)
+          tma_load_im2col_4d(b_dst + (uint32_t)(j * WT_BOX), &tmap_x, ci0 + j * 64, ow0 - pad, oh0 - pad, b, (uint16_t)(tap % ks), (uint16_t)(tap / ks), &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, BLOCK_N) | (1u << 15) | (1u << 16);  // A and B MN-major
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < nk; kb++) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + s * A_STAGE), b_base = smem_u32(sB + s * B_STAGE);
+#pragma unroll
+        for (int k = 0; k < WT_K / 16; k++)
+          umma_bf16(tacc, make_smem_desc_mn_sw128(a_base + k * 2048, WT_BOX), make_smem_desc_mn_sw128(b_base + k * 2048, WT_BOX), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty[s]);
+        if (kb == nk - 1) umma_commit(acc_full);
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    const int quarter = warp & 3, co = co0 + quarter * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    float* dst_row = part + (((size_t)b * Cout + (co < Cout ? co : 0)) * taps + tap) * Cin + ci0;
+    for (int cb = 0; cb < BLOCK_N; cb += 32) {
+      float v[32];
+      tmem_ld32(tacc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cb, v);
+      if (co < Cout) {
+        float4* dst = (float4*)(dst_row + cb);
+#pragma unroll
+        for (int j = 0; j < 8; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tacc, BLOCK_N);
+}
+
+// 3-D tiled tensor map of dY [B][H*W][Cout] bf16 (innermost first: Cout, H*W, B) with a [64 channels x 128 pixels x 1 image] box
+typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_dy_tmap(CUtensorMap* m, const void* dy, int B, int HW, int Cout) {
+  static EncodeTiledFn3 fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn3)p;
+  }
+  if (!fn) { snprintf(q_err, sizeof q_err, "cuTensorMapEncodeTiled is not available"); return -3; }
+  cuuint64_t gdim[3] = {(cuuint64_t)Cout, (cuuint64_t)HW, (cuuint64_t)B};
+  cuuint64_t gstride[2] = {(cuuint64_t)Cout * 2, (cuuint64_t)HW * Cout * 2};
+  cuuint32_t box[3] = {64, WT_K, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(dy), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(q_err, sizeof q_err, "cuTensorMapEncodeTiled (dY) failed (%d)", (int)r); return -3; }
+  return 0;
+}
+// -> 0 launched, 1 not available on this driver (caller uses k_wgrad), < 0 error
+static int launch_wgrad_tc(cudaStream_t st, const void* dY, const void* x, float* part, int B, int H, int W, int Cin, int Cout, int ks) {
+  alignas(64) CUtensorMap tdy, tx;
+  memset(&tdy, 0, sizeof tdy); memset(&tx, 0, sizeof tx);
+  if (make_dy_tmap(&tdy, dY, B, H * W, Cout) != 0 || make_act_tmap_im2col(&tx, x, B, H, W, Cin, ks) != 0) return 1;
+  const int taps = ks * ks;
+#define LAUNCH_WT(BN_, ST_)                                                                                                   \
+  do {                                                                                                                        \
+    const size_t smem = (size_t)ST_ * (2 * WT_BOX + (BN_ / 64) * WT_BOX) + 8 * (2 * ST_ + 1) + 16;                              \
+    QCK(cudaFuncSetAttribute(k_wgrad_tc<BN_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
+    dim3 grid((Cout + 127) / 128, Cin / BN_, taps * B);                                                                       \
+    k_wgrad_tc<BN_, ST_><<<grid, 192, smem, st>>>(tdy, tx, part, H, W, Cin, Cout, ks);                                         \
+  } while (0)
+  if (Cin % 128 == 0) LAUNCH_WT(128, 3);
+  else LAUNCH_WT(64, 4);
+#undef LAUNCH_WT
+  return 0;
+}
+
 // scratch_part of gq_bn_relu_bwd: ceil(B*HW / 128) * C * 2 floats
 extern "C" int gq_conv_wgrad(const void* dY, const void* x, float* scratch_part, float* dW, int B, int H, int W, int Cin, int Cout, int ks, void* stream) {
   if (!dY || !x || !scratch_part || !dW || (ks != 1 && ks != 3) || Cin % 64 || Cout % 64) { snprintf(q_err, sizeof q_err, "gq_conv_wgrad: bad argument"); return -1; }
   cudaStream_t st = (cudaStream_t)stream;
   const int taps = ks * ks;
-  dim3 grid(Cout / WG_T, Cin / WG_T, taps * B);
-  k_wgrad<<<grid, 256, 0, st>>>((const bf16*)dY, (const bf16*)x, scratch_part, H, W, Cin, Cout, ks);
+  // tcgen05 path by default (GQ_WGRAD_TC=0: the CUDA-core kernel, kept as the A/B partner and for drivers without the tensor-map encoders)
+  const char* e_tc = getenv("GQ_WGRAD_TC");  // (read per call: the parity test switches between the two kernels inside one process)
+  const int use_tc = (e_tc && atoi(e_tc) == 0) ? 0 : 1;
+  int r = use_tc ? launch_wgrad_tc(st, dY, x, scratch_part, B, H, W, Cin, Cout, ks) : 1;
+  if (r < 0) return r;
+  if (r == 1) {
+    dim3 grid(Cout / WG_T, Cin / WG_T, taps * B);
+    k_wgrad<<<grid, 256, 0, st>>>((const bf16*)dY, (const bf16*)x, scratch_part, H, W, Cin, Cout, ks);
+  }
   const size_t n = (size_t)Cout * taps * Cin;
   k_reduce_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scratch_part, dW, B, n);
   QCK(cudaGetLastError());
@@ -359,7 +531,7 @@ extern "C" int gq_conv_first_wgrad(const void* dY, const float* x, float* scratc
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)B * H * W;
   const int ppc = 2048, chunks = (int)((n + ppc - 1) / ppc);
-  k_conv_first_wgrad<<<dim3(36, chunks), 64, 0, st>>>((const bf16*)dY, x, scratch_part, B, H, W, ppc);
+  k_conv_first_wgrad<<<chunks, 256, 0, st>>>((const bf16*)dY, x, scratch_part, B, H, W, ppc);
   k_reduce_rows<<<(64 * 36 + 127) / 128, 128, 0, st>>>(scratch_part, dW, chunks, (size_t)64 * 36);
   QCK(cudaGetLastError());
   return 0;

@@ -89,8 +89,12 @@ def _bf(x):
 
 
 @gpu
-@pytest.mark.parametrize("ks,cin,cout,H,W", [(3, 64, 128, 20, 24), (1, 128, 64, 17, 9), (3, 128, 256, 10, 10)])
-def test_wgrad_and_dgrad_match_autograd(learner, ks, cin, cout, H, W):
+@pytest.mark.parametrize("ks,cin,cout,H,W", [(3, 64, 128, 20, 24), (1, 128, 64, 17, 9), (3, 128, 256, 10, 10), (3, 64, 64, 25, 25), (3, 256, 128, 30, 7),
+                                             (1, 512, 256, 16, 16)])
+@pytest.mark.parametrize("tc", [1, 0])
+def test_wgrad_and_dgrad_match_autograd(learner, ks, cin, cout, H, W, tc, monkeypatch):
+    """tc = 1: the tcgen05 weight-gradient kernel (default); tc = 0: its CUDA-core A/B partner (GQ_WGRAD_TC=0)"""
+    monkeypatch.setenv("GQ_WGRAD_TC", str(tc))
     B = 3
     g = torch.Generator(device="cuda").manual_seed(1)
     x = _bf(torch.randn((B, H, W, cin), generator=g, device="cuda"))
@@ -110,6 +114,23 @@ def test_wgrad_and_dgrad_match_autograd(learner, ks, cin, cout, H, W):
     wT = wb.float().flip(2, 3).permute(1, 2, 3, 0).contiguous().to(torch.bfloat16)
     dx = learner._dgrad(dY.reshape(B, H * W, cout), wT.reshape(cin, ks * ks, cout), B, H, W, cin, cout, ks)
     assert rel(dx.view(B, H, W, cin).permute(0, 3, 1, 2), xr.grad) < 2e-3
+
+
+@gpu
+@pytest.mark.parametrize("H,W", [(20, 24), (50, 47)])
+def test_first_conv_wgrad_matches_autograd(learner, H, W):
+    """gq_conv_first_wgrad (4 -> 64 channels, f32 NCHW input) against autograd of F.conv2d on the same values"""
+    B = 3
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((B, 4, H, W), generator=g, device="cuda")
+    dY = _bf(torch.randn((B, H, W, 64), generator=g, device="cuda"))
+    wr = torch.zeros((64, 4, 3, 3), device="cuda", requires_grad=True)
+    F.conv2d(x, wr, padding=1).backward(dY.float().permute(0, 3, 1, 2))
+    n = B * H * W
+    part = torch.empty(((n + 2047) // 2048) * 64 * 36, dtype=torch.float32, device="cuda")
+    dW = torch.empty((64, 9, 4), dtype=torch.float32, device="cuda")
+    learner._ck(learner.L.gq_conv_first_wgrad(learner._p(dY), learner._p(x), learner._p(part), learner._p(dW), B, H, W, learner._st()), "gq_conv_first_wgrad")
+    assert rel(dW.view(64, 3, 3, 4).permute(0, 3, 1, 2), wr.grad) < 1e-4
 
 
 @gpu
