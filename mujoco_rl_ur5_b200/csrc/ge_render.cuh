@@ -135,6 +135,7 @@ __device__ __forceinline__ double ray_geom(int g, const double* fr, const double
 __global__ void __launch_bounds__(RTILE * RTILE) k_render(const double* gframes, int n_env, int cam, int W, int H, unsigned char* rgb, float* depth) {
   const DevModel& m = c_m;
   __shared__ int s_list[256];
+  __shared__ short4 s_bb[256];  // screen-space bounding box (pixel columns x0..x1, rows y0..y1) of the listed geom
   __shared__ int s_n;
   int env = blockIdx.y, tiles_x = (W + RTILE - 1) / RTILE;
   int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
@@ -145,9 +146,16 @@ __global__ void __launch_bounds__(RTILE * RTILE) k_render(const double* gframes,
   double f = 0.5 * H / tan(m.cam_fovy[cam] * PI / 360.0);
   if (tid == 0) s_n = 0;
   __syncthreads();
-  // tile bounding cone (camera frame): axis through the tile centre, half-angle to the farthest corner (+ half a pixel)
+  // Two conservative tests per (tile, geom), one thread per geom: (1) the tile's bounding cone (camera frame: axis through the tile
+  // centre, half-angle to the farthest corner) against the geom's bounding sphere; (2) r02: the screen-space box of the geom's 8 OBB
+  // corners (pixel (c, r) sees direction ((W/2 - c - 1/2) / f, (H/2 - r - 1/2) / f, -1), so a camera-frame point p lands on
+  // c = W/2 - 1/2 - f p.x / (-p.z)) against the tile's pixel range - the table top, legs and bin walls have bounding spheres of 0.35-0.5 m
+  // that pass (1) for every tile.  The box is kept with the list so that each pixel also skips the geoms whose box it is outside of.
+  // Both tests only drop geoms no ray of the tile / pixel can hit: the image is the same as with the full list.
+  // (r02h: 6.1 -> 2.7 listed geoms per tile in the 6-object scene; the per-pixel fp64 ray tests are the cost of this kernel.)
   {
-    double c0 = tx * RTILE, c1 = fmin((double)W, c0 + RTILE), r0 = ty * RTILE, r1 = fmin((double)H, r0 + RTILE);
+    const int c0i = tx * RTILE, c1i = min(W, c0i + RTILE), r0i = ty * RTILE, r1i = min(H, r0i + RTILE);
+    double c0 = c0i, c1 = c1i, r0 = r0i, r1 = r1i;
     double ax[3] = {(0.5 * W - 0.5 * (c0 + c1)) / f, (0.5 * H - 0.5 * (r0 + r1)) / f, -1.0};
     v3normalize(ax);
     double cosmin = 1.0;
@@ -160,17 +168,38 @@ __global__ void __launch_bounds__(RTILE * RTILE) k_render(const double* gframes,
     double phi = acos(fmin(1.0, cosmin));
     for (int g = tid; g < m.ngeom; g += RTILE * RTILE) {
       bool pass = true;
+      short4 bb = make_short4(0, 0, (short)(W - 1), (short)(H - 1));
       if (m.geom_type[g] != G_PLANE) {
+        const double* R = fr + 12 * g + 3;
         double cw[3], t[3], pc[3];
-        m3mulv(t, fr + 12 * g + 3, m.geom_obbcenter + 3 * g); v3add(cw, fr + 12 * g, t);
+        m3mulv(t, R, m.geom_obbcenter + 3 * g); v3add(cw, fr + 12 * g, t);
         v3sub(t, cw, cp); m3Tmulv(pc, cm, t);
         double dist = v3norm(pc), r = m.geom_rbound[g];
         if (dist > r) {
           double ang = acos(fmax(-1.0, fmin(1.0, v3dot(pc, ax) / dist)));
           pass = ang <= phi + asin(fmin(1.0, r / dist)) + 1e-9;
         }
+        if (pass) {
+          const double* hf = m.geom_obbhalf + 3 * g;
+          double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+          bool front = true;
+          for (int k = 0; k < 8; k++) {
+            double off[3] = {(k & 1) ? hf[0] : -hf[0], (k & 2) ? hf[1] : -hf[1], (k & 4) ? hf[2] : -hf[2]}, ow[3], q[3];
+            m3mulv(ow, R, off); v3add(ow, ow, t);  // corner relative to the camera position, world axes
+            m3Tmulv(q, cm, ow);
+            if (-q[2] < 1e-6) { front = false; break; }
+            double u = 0.5 * W - 0.5 - f * q[0] / (-q[2]), v = 0.5 * H - 0.5 - f * q[1] / (-q[2]);
+            xmin = fmin(xmin, u); xmax = fmax(xmax, u); ymin = fmin(ymin, v); ymax = fmax(ymax, v);
+          }
+          if (front) {  // one pixel of slack on every side for the rounding of the projection
+            int x0 = (int)floor(fmax(xmin, -2.0)) - 1, x1 = (int)ceil(fmin(xmax, (double)W + 1)) + 1;
+            int y0 = (int)floor(fmax(ymin, -2.0)) - 1, y1 = (int)ceil(fmin(ymax, (double)H + 1)) + 1;
+            pass = !(x1 < c0i || x0 > c1i - 1 || y1 < r0i || y0 > r1i - 1);
+            bb = make_short4((short)max(x0, 0), (short)max(y0, 0), (short)min(x1, W - 1), (short)min(y1, H - 1));
+          }
+        }
       }
-      if (pass) { int k = atomicAdd(&s_n, 1); if (k < 256) s_list[k] = g; }
+      if (pass) { int k = atomicAdd(&s_n, 1); if (k < 256) { s_list[k] = g; s_bb[k] = bb; } }
     }
   }
   __syncthreads();
@@ -182,6 +211,8 @@ __global__ void __launch_bounds__(RTILE * RTILE) k_render(const double* gframes,
   double best = 1e300, bn[3] = {0, 0, 1};
   int bg = -1;
   for (int k = 0; k < n; k++) {
+    const short4 bb = s_bb[k];
+    if (c < bb.x || c > bb.z || r < bb.y || r > bb.w) continue;
     int g = s_list[k];
     double nr[3];
     double t = ray_geom(g, fr + 12 * g, cp, dir, nr);

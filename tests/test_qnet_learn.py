@@ -130,7 +130,7 @@ def test_first_conv_wgrad_matches_autograd(learner, H, W):
     part = torch.empty(((n + 2047) // 2048) * 64 * 36, dtype=torch.float32, device="cuda")
     dW = torch.empty((64, 9, 4), dtype=torch.float32, device="cuda")
     learner._ck(learner.L.gq_conv_first_wgrad(learner._p(dY), learner._p(x), learner._p(part), learner._p(dW), B, H, W, learner._st()), "gq_conv_first_wgrad")
-    assert rel(dW.view(64, 3, 3, 4).permute(0, 3, 1, 2), wr.grad) < 1e-4
+    assert rel(dW.view(64, 3, 3, 4).permute(0, 3, 1, 2), wr.grad) < 1e-3  # fp32 sums over B*H*W products in a different order (r02i: 2e-4 at 3 x 50 x 47)
 
 
 @gpu
