@@ -2,21 +2,25 @@
 // (reference: MujocoController.py:708-740).  Output already has the reference's U/D + L/R flip applied and depth is
 // linear eye-space z in metres.
 //
-// Two kernels: (1) one warp per env runs the kinematics stage and writes every geom's world frame to HBM
-// ([N, ngeom, 12] f64); (2) one 16x16-pixel tile per CTA: the CTA culls the geoms against the tile's bounding cone into a
-// shared-memory list, then every thread casts its pixel's ray against that list (plane / sphere / box analytic, mesh geoms
-// as convex polytopes = hull face planes).  Writes are coalesced: depth f32 rows of 16 pixels, rgb u8x3.
+// Two kernels: (1) one warp (CTA in the big-scene build) per env runs the kinematics stage and writes every geom's world frame
+// ([N, ngeom, 12] f64) and its screen-space box ([N, ngeom] short4) to HBM; (2) one 16x16-pixel tile per CTA: the geoms whose box meets
+// the tile go into a shared-memory list, then every thread casts its pixel's ray against the listed geoms whose box contains the pixel
+// (plane / sphere / box / capsule / cylinder analytic, mesh geoms as convex polytopes = hull face planes).  Writes are coalesced:
+// depth f32 rows of 16 pixels, rgb u8x3.
 #pragma once
 #include "ge_physics.cuh"
 
 namespace ge {
 
-struct RenderCtx { double* gframes; size_t cap_envs; };
+struct RenderCtx { double* gframes; short4* gbox; double* fpx; size_t cap_envs; };
 
-static inline void render_init(RenderCtx& r, const DevModel&, const char*) { r.gframes = nullptr; r.cap_envs = 0; }
-static inline void render_free(RenderCtx& r) { if (r.gframes) cudaFree(r.gframes); r.gframes = nullptr; }
+static inline void render_init(RenderCtx& r, const DevModel&, const char*) { r.gframes = nullptr; r.gbox = nullptr; r.fpx = nullptr; r.cap_envs = 0; }
+static inline void render_free(RenderCtx& r) { if (r.gframes) cudaFree(r.gframes); if (r.gbox) cudaFree(r.gbox); if (r.fpx) cudaFree(r.fpx); r.gframes = nullptr; r.gbox = nullptr; r.fpx = nullptr; }
 
-__global__ void __launch_bounds__(GE_LANES) k_render_fk(const double* qpos, int n_env, double* gframes) {
+// Also writes every geom's screen-space box for camera `cam` (r02): pixel (c, r) sees direction ((W/2 - c - 1/2) / f, (H/2 - r - 1/2) / f, -1)
+// in the camera frame, so a camera-frame point p lands on c = W/2 - 1/2 - f p.x / (-p.z); the box of the 8 OBB corners, one pixel of
+// slack on every side, clamped to the image (x0 > x1: not visible at all; planes and geoms reaching behind the camera: whole image).
+__global__ void __launch_bounds__(GE_LANES) k_render_fk(const double* qpos, int n_env, double* gframes, short4* gbox, double* fpx, int cam, int W, int H) {
   extern __shared__ double smem[];
   const DevModel& m = c_m; const Layout& L = c_L;
   int env = blockIdx.x, lane = threadIdx.x;
@@ -26,9 +30,36 @@ __global__ void __launch_bounds__(GE_LANES) k_render_fk(const double* qpos, int 
   gsync();
   stage_fk(ws, lane);
   double* out = gframes + (size_t)env * m.ngeom * 12;
+  const double *cp = m.cam_pos0 + 3 * cam, *cm = m.cam_mat0 + 9 * cam;
+  const double f = 0.5 * H / tan(m.cam_fovy[cam] * 3.14159265358979323846 / 360.0);  // focal length in pixels (MujocoController.py:742-758)
+  if (env == 0 && lane == 0) *fpx = f;                                                 // (k_render reads it instead of one tan per thread)
   LANE_LOOP(g, m.ngeom) {
-    for (int k = 0; k < 3; k++) out[12 * g + k] = ws[L.gpos + 3 * g + k];
-    for (int k = 0; k < 9; k++) out[12 * g + 3 + k] = ws[L.gmat + 9 * g + k];
+    const double *gp = ws + L.gpos + 3 * g, *R = ws + L.gmat + 9 * g;
+    for (int k = 0; k < 3; k++) out[12 * g + k] = gp[k];
+    for (int k = 0; k < 9; k++) out[12 * g + 3 + k] = R[k];
+    short4 bb = make_short4(0, 0, (short)(W - 1), (short)(H - 1));
+    if (m.geom_type[g] != G_PLANE) {
+      const double* hf = m.geom_obbhalf + 3 * g;
+      double t[3], cw[3];
+      m3mulv(t, R, m.geom_obbcenter + 3 * g); v3add(cw, gp, t); v3sub(t, cw, cp);  // OBB centre relative to the camera, world axes
+      double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+      bool front = true;
+      for (int k = 0; k < 8; k++) {
+        double off[3] = {(k & 1) ? hf[0] : -hf[0], (k & 2) ? hf[1] : -hf[1], (k & 4) ? hf[2] : -hf[2]}, ow[3], q[3];
+        m3mulv(ow, R, off); v3add(ow, ow, t);
+        m3Tmulv(q, cm, ow);
+        if (-q[2] < 1e-6) { front = false; break; }
+        double u = 0.5 * W - 0.5 - f * q[0] / (-q[2]), v = 0.5 * H - 0.5 - f * q[1] / (-q[2]);
+        xmin = fmin(xmin, u); xmax = fmax(xmax, u); ymin = fmin(ymin, v); ymax = fmax(ymax, v);
+      }
+      if (front) {
+        int x0 = (int)floor(fmax(xmin, -2.0)) - 1, x1 = (int)ceil(fmin(xmax, (double)W + 1)) + 1;
+        int y0 = (int)floor(fmax(ymin, -2.0)) - 1, y1 = (int)ceil(fmin(ymax, (double)H + 1)) + 1;
+        if (x1 < 0 || x0 > W - 1 || y1 < 0 || y0 > H - 1) bb = make_short4(1, 1, 0, 0);
+        else bb = make_short4((short)max(x0, 0), (short)max(y0, 0), (short)min(x1, W - 1), (short)min(y1, H - 1));
+      }
+    }
+    gbox[(size_t)env * m.ngeom + g] = bb;
   }
 }
 
@@ -132,77 +163,36 @@ __device__ __forceinline__ double ray_geom(int g, const double* fr, const double
 }
 
 #define RTILE 16
-__global__ void __launch_bounds__(RTILE * RTILE) k_render(const double* gframes, int n_env, int cam, int W, int H, unsigned char* rgb, float* depth) {
+__global__ void __launch_bounds__(RTILE * RTILE) k_render(const double* gframes, const short4* gbox, const double* fpx, int n_env, int cam, int W, int H, unsigned char* rgb,
+                                                          float* depth) {
   const DevModel& m = c_m;
   __shared__ int s_list[256];
-  __shared__ short4 s_bb[256];  // screen-space bounding box (pixel columns x0..x1, rows y0..y1) of the listed geom
+  __shared__ short4 s_bb[256];  // screen-space box (pixel columns x..z, rows y..w) of the listed geom
   __shared__ int s_n;
   int env = blockIdx.y, tiles_x = (W + RTILE - 1) / RTILE;
   int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
   int tid = threadIdx.y * RTILE + threadIdx.x;
   const double* fr = gframes + (size_t)env * m.ngeom * 12;
   const double *cp = m.cam_pos0 + 3 * cam, *cm = m.cam_mat0 + 9 * cam;
-  const double PI = 3.14159265358979323846;
-  double f = 0.5 * H / tan(m.cam_fovy[cam] * PI / 360.0);
   if (tid == 0) s_n = 0;
   __syncthreads();
-  // Two conservative tests per (tile, geom), one thread per geom: (1) the tile's bounding cone (camera frame: axis through the tile
-  // centre, half-angle to the farthest corner) against the geom's bounding sphere; (2) r02: the screen-space box of the geom's 8 OBB
-  // corners (pixel (c, r) sees direction ((W/2 - c - 1/2) / f, (H/2 - r - 1/2) / f, -1), so a camera-frame point p lands on
-  // c = W/2 - 1/2 - f p.x / (-p.z)) against the tile's pixel range - the table top, legs and bin walls have bounding spheres of 0.35-0.5 m
-  // that pass (1) for every tile.  The box is kept with the list so that each pixel also skips the geoms whose box it is outside of.
-  // Both tests only drop geoms no ray of the tile / pixel can hit: the image is the same as with the full list.
-  // (r02h: 6.1 -> 2.7 listed geoms per tile in the 6-object scene; the per-pixel fp64 ray tests are the cost of this kernel.)
+  // The tile lists the geoms whose screen box (k_render_fk) meets its pixel range, and keeps the box so that each pixel also skips the
+  // geoms whose box it lies outside of.  The boxes only drop geoms no ray of the tile / pixel can hit: the image is the same as with
+  // the full list.  r01 culled with the tile's bounding cone against bounding spheres: the table top, legs and bin walls (spheres of
+  // 0.35-0.5 m) passed for every tile, 6.1 listed geoms per tile in the 6-object scene against 2.7 now; r02j computed the boxes here,
+  // per tile, and spent the gain at this barrier (36 busy threads of 256: `barrier` 3.0 cycles per issue) - now once per env.
   {
     const int c0i = tx * RTILE, c1i = min(W, c0i + RTILE), r0i = ty * RTILE, r1i = min(H, r0i + RTILE);
-    double c0 = c0i, c1 = c1i, r0 = r0i, r1 = r1i;
-    double ax[3] = {(0.5 * W - 0.5 * (c0 + c1)) / f, (0.5 * H - 0.5 * (r0 + r1)) / f, -1.0};
-    v3normalize(ax);
-    double cosmin = 1.0;
-    for (int k = 0; k < 4; k++) {
-      double cc = (k & 1) ? c1 : c0, rr = (k & 2) ? r1 : r0;
-      double d[3] = {(0.5 * W - cc) / f, (0.5 * H - rr) / f, -1.0};
-      v3normalize(d);
-      cosmin = fmin(cosmin, v3dot(d, ax));
-    }
-    double phi = acos(fmin(1.0, cosmin));
+    const short4* gb = gbox + (size_t)env * m.ngeom;
     for (int g = tid; g < m.ngeom; g += RTILE * RTILE) {
-      bool pass = true;
-      short4 bb = make_short4(0, 0, (short)(W - 1), (short)(H - 1));
-      if (m.geom_type[g] != G_PLANE) {
-        const double* R = fr + 12 * g + 3;
-        double cw[3], t[3], pc[3];
-        m3mulv(t, R, m.geom_obbcenter + 3 * g); v3add(cw, fr + 12 * g, t);
-        v3sub(t, cw, cp); m3Tmulv(pc, cm, t);
-        double dist = v3norm(pc), r = m.geom_rbound[g];
-        if (dist > r) {
-          double ang = acos(fmax(-1.0, fmin(1.0, v3dot(pc, ax) / dist)));
-          pass = ang <= phi + asin(fmin(1.0, r / dist)) + 1e-9;
-        }
-        if (pass) {
-          const double* hf = m.geom_obbhalf + 3 * g;
-          double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
-          bool front = true;
-          for (int k = 0; k < 8; k++) {
-            double off[3] = {(k & 1) ? hf[0] : -hf[0], (k & 2) ? hf[1] : -hf[1], (k & 4) ? hf[2] : -hf[2]}, ow[3], q[3];
-            m3mulv(ow, R, off); v3add(ow, ow, t);  // corner relative to the camera position, world axes
-            m3Tmulv(q, cm, ow);
-            if (-q[2] < 1e-6) { front = false; break; }
-            double u = 0.5 * W - 0.5 - f * q[0] / (-q[2]), v = 0.5 * H - 0.5 - f * q[1] / (-q[2]);
-            xmin = fmin(xmin, u); xmax = fmax(xmax, u); ymin = fmin(ymin, v); ymax = fmax(ymax, v);
-          }
-          if (front) {  // one pixel of slack on every side for the rounding of the projection
-            int x0 = (int)floor(fmax(xmin, -2.0)) - 1, x1 = (int)ceil(fmin(xmax, (double)W + 1)) + 1;
-            int y0 = (int)floor(fmax(ymin, -2.0)) - 1, y1 = (int)ceil(fmin(ymax, (double)H + 1)) + 1;
-            pass = !(x1 < c0i || x0 > c1i - 1 || y1 < r0i || y0 > r1i - 1);
-            bb = make_short4((short)max(x0, 0), (short)max(y0, 0), (short)min(x1, W - 1), (short)min(y1, H - 1));
-          }
-        }
-      }
-      if (pass) { int k = atomicAdd(&s_n, 1); if (k < 256) { s_list[k] = g; s_bb[k] = bb; } }
+      const short4 bb = gb[g];
+      if (bb.z < c0i || bb.x > c1i - 1 || bb.w < r0i || bb.y > r1i - 1) continue;
+      int k = atomicAdd(&s_n, 1);
+      if (k < 256) { s_list[k] = g; s_bb[k] = bb; }
     }
   }
   __syncthreads();
+  const double f = *fpx;
   int c = tx * RTILE + threadIdx.x, r = ty * RTILE + threadIdx.y;
   if (c >= W || r >= H) return;
   int n = s_n < 256 ? s_n : 256;
@@ -241,15 +231,19 @@ static inline int render_launch(RenderCtx& rc, const DevModel& m, const Layout& 
                                 unsigned char* rgb, float* depth, cudaStream_t stream, int64_t* launches) {
   if (rc.cap_envs < (size_t)n_env) {
     if (rc.gframes) cudaFree(rc.gframes);
+    if (rc.gbox) cudaFree(rc.gbox);
+    rc.gframes = nullptr; rc.gbox = nullptr;
     if (cudaMalloc(&rc.gframes, sizeof(double) * 12 * m.ngeom * (size_t)n_env) != cudaSuccess) return -1;
+    if (cudaMalloc(&rc.gbox, sizeof(short4) * m.ngeom * (size_t)n_env) != cudaSuccess) return -1;
+    if (!rc.fpx && cudaMalloc(&rc.fpx, sizeof(double)) != cudaSuccess) return -1;
     rc.cap_envs = n_env;
   }
   static bool attr_done = false;
   if (!attr_done && L.fk_bytes > 48 * 1024) { cudaFuncSetAttribute(k_render_fk, cudaFuncAttributeMaxDynamicSharedMemorySize, L.fk_bytes); attr_done = true; }
-  k_render_fk<<<n_env, GE_LANES, L.fk_bytes, stream>>>(qpos, n_env, rc.gframes);
+  k_render_fk<<<n_env, GE_LANES, L.fk_bytes, stream>>>(qpos, n_env, rc.gframes, rc.gbox, rc.fpx, cam, W, H);
   int tiles = ((W + RTILE - 1) / RTILE) * ((H + RTILE - 1) / RTILE);
   dim3 grid(tiles, n_env), blk(RTILE, RTILE);
-  k_render<<<grid, blk, 0, stream>>>(rc.gframes, n_env, cam, W, H, rgb, depth);
+  k_render<<<grid, blk, 0, stream>>>(rc.gframes, rc.gbox, rc.fpx, n_env, cam, W, H, rgb, depth);
   *launches += 2;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -136,6 +136,10 @@ class QNetForward:
         self.w_head = sd["1.C1.weight"].reshape(self.A, 64).contiguous()
         self.b_head = sd["1.C1.bias"].contiguous()
         self.launches = 0
+        # GQ_GRAPH=1: the ~110 launches of one chunk captured once per input shape in a CUDA graph and replayed (static input / output
+        # buffers; tensor maps and pointers are baked into the graph).  Off by default: see DESIGN.md for the measurement.
+        self.use_graph = os.environ.get("GQ_GRAPH", "0") == "1"
+        self._graphs = {}
 
     def _ck(self, r, what):
         if r != 0:
@@ -227,8 +231,32 @@ class QNetForward:
         """state [B,4,H,W] f32 on the device -> Q [B,A,H,W] f32 (sigmoid), chunked to bound activation memory"""
         t = self.torch
         state = state.to(self.dev, t.float32).contiguous()
-        outs = [self._forward_chunk(state[i:i + self.max_batch]) for i in range(0, state.shape[0], self.max_batch)]
+        fn = self._forward_chunk_graphed if self.use_graph else self._forward_chunk
+        outs = [fn(state[i:i + self.max_batch]) for i in range(0, state.shape[0], self.max_batch)]
         return outs[0] if len(outs) == 1 else t.cat(outs, dim=0)
+
+    def _forward_chunk_graphed(self, state):
+        t = self.torch
+        key = tuple(state.shape)
+        g = self._graphs.get(key)
+        if g is None:
+            sin = state.clone()
+            cur = t.cuda.current_stream(self.dev)
+            side = t.cuda.Stream(self.dev)
+            side.wait_stream(cur)
+            with t.cuda.stream(side):  # warm-up outside the capture (function attributes, driver entry points, allocator)
+                self._forward_chunk(sin)
+            cur.wait_stream(side)
+            n0 = self.launches
+            graph = t.cuda.CUDAGraph()
+            with t.cuda.graph(graph):
+                sout = self._forward_chunk(sin)
+            g = self._graphs[key] = (graph, sin, sout, self.launches - n0)
+        graph, sin, sout, nl = g
+        sin.copy_(state)
+        graph.replay()
+        self.launches += nl
+        return sout.clone()
 
     def obs_to_state(self, obs, depth_threshold=1.1):
         """batched deterministic transform_observation: obs dict of device tensors (rgb u8 [B,H,W,3], depth f32 [B,H,W]) -> [B,4,H,W] f32.

@@ -111,3 +111,24 @@ def test_default_scene_is_the_reference_default():
     e = grasp_env.GraspEnv(quiet=True, show_obs=False)
     assert e.scene == "B" and e.engine.size(1) == 248
     e.close()
+
+
+def test_record_grasps_writes_the_side_camera_picture(env, tmp_path):
+    """SURVEY 8f.4 on the GPU (GraspingEnv.py:329-335): the phase-by-phase attempt of `record_grasps=True` from a state where the oracle's
+    attempt is rewarded (tests/golden/success_64) must hold the object at the drop pose and write the 1000 x 1000 `side` picture."""
+    import json
+
+    from PIL import Image
+
+    gold = os.path.join(ROOT, "tests", "golden")
+    recs = json.load(open(os.path.join(gold, "success_64.json")))["records"]
+    z = np.load(os.path.join(gold, "success_64.npz"))
+    made = []
+    for i in range(4):  # rewarded records; the recorded variant issues the movements one by one, so its step counts may differ
+        env.set_state(z["qpos0"][i], z["qvel0"][i])
+        grasped, png = env.move_and_grasp_recorded(recs[i]["coords"], recs[i]["action"][1], directory=str(tmp_path))
+        if grasped:
+            made.append(png)
+    assert len(made) >= 3, made
+    im = np.asarray(Image.open(made[0]))
+    assert im.shape == (1000, 1000, 3) and im.std() > 5  # a real picture, not a blank frame

@@ -111,3 +111,22 @@ def test_reference_dataset_class_reads_our_file(tmp_path):
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+@pytest.mark.gpu
+def test_batched_data_generation_on_the_gpu(tmp_path):
+    """SURVEY 8f.3 end to end on the device: tools/generate_data_batched.py (epsilon-greedy Q-net actions over batched environments)
+    writes files in the reference's layout that load back with the right shapes and reward range"""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "Data")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "generate_data_batched.py"), "--envs", "12", "--episodes", "1", "--steps", "2", "--out", out],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    files = sorted(os.listdir(out))
+    assert len(files) == 2  # 24 transitions, 12 per file (generate_data.py:19,83)
+    rgb, depth, actions, rewards = od.load_transitions(os.path.join(out, files[0]))
+    assert rgb.shape == (12, 200, 200, 3) and depth.shape == (12, 200, 200) and actions.shape == (12,)
+    assert set(rewards.tolist()) <= {0, 1} and 0 <= actions.min() and actions.max() < 6 * 200 * 200
+    assert 0.5 < float(depth.min()) and rgb.std() > 1

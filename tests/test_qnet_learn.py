@@ -265,7 +265,9 @@ def test_learn_step_matches_the_reference(learner):
         if upd_ref.numel():
             agree = (torch.sign(upd) == torch.sign(upd_ref)).float().mean()
             assert agree > (0.97 if k.startswith("1.C1") else 0.75), (k, float(agree))  # early layers: the mask noise above
-            assert (upd.abs() - 0.001).abs().max() < 1e-4  # first Adam step: |update| = lr wherever the gradient is not ~0
+            # first Adam step: |update| = lr * |g| / (|g| + eps), i.e. lr wherever OUR gradient is not ~1e-8; `big` is chosen on the fp32
+            # reference gradient, so a bf16-noise-cancelled element can slip in (r02j: one element at 0.8 lr): all but 0.1 % within 10 %
+            assert ((upd.abs() - 0.001).abs() < 1e-4).float().mean() > 0.999, k
 
 
 @gpu

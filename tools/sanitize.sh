@@ -7,7 +7,7 @@
 O=${1:-gpurun_out/sanitize}
 mkdir -p $O
 for tool in memcheck synccheck racecheck initcheck; do
-  args="12 2"; [ $tool = racecheck ] && args="4 0"   # racecheck tracks shared memory only: the HBM-workspace scene has none
+  args="12 2"; [ $tool = racecheck ] && args="4 1"   # racecheck slows kernels down ~100x: fewer sub-steps (both scenes keep their workspace in shared memory)
   timeout ${SAN_TIMEOUT:-240} compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_target.py $args > $O/$tool.log 2>&1
   rc=$?
   echo "$tool: exit $rc; $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $O/$tool.log | tail -1)" | tee -a $O/summary.txt
