@@ -422,7 +422,10 @@ def run_ours(args):
         rw = (torch.rand(lb, 1, generator=g) < 0.3).float().to(dev)
         import torch.distributed as dist
 
-        learner = QNetLearner(seed=0, device=local, process_group=dist.group.WORLD if world > 1 else None)
+        # the per-group gradient all-reduce (NCCL) is part of the step only on request: it is checked by tools/learner_2gpu_check.py, and the
+        # default multi-rank bench line must not depend on it
+        use_pg = world > 1 and os.environ.get("BENCH_LEARN_ALLREDUCE", "0") == "1"
+        learner = QNetLearner(seed=0, device=local, process_group=dist.group.WORLD if use_pg else None)
         for _ in range(2):
             learner.learn_step(st, ac, rw)
         barrier()
@@ -437,7 +440,7 @@ def run_ours(args):
         ltf = lb * 3 * 41.99424e9 / (lms * 1e-3) / 1e12  # forward + dgrad + wgrad ~ 3x the forward MACs
         linfo = {"batch_per_gpu": lb, "ms_per_update": lms, "updates_per_s": 1e3 / lms, "transitions_per_s": world * lb * 1e3 / lms, "tflops_per_gpu": ltf,
                  "kernels_per_update": (learner.launches - l_l0) // max(args.qnet_reps, 1), "loss": loss_l,
-                 "collective": ("all_reduce of %.1f MB fp32 gradients over %d ranks (NCCL)" % (learner.grad.numel() * 4 / 1e6, world)) if world > 1 else None,
+                 "collective": ("all_reduce of %.1f MB fp32 gradients over %d ranks (NCCL)" % (learner.grad.numel() * 4 / 1e6, world)) if use_pg else None,
                  "note": "QNetLearner.learn_step: forward (tcgen05) with batch-statistics BN, gather-BCE, dgrad (tcgen05), wgrad (CUDA-core tiles), Adam; "
                          "includes the loss .item() read like the reference"}
         del learner, st, ac, rw

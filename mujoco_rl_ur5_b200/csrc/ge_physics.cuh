@@ -771,6 +771,9 @@ __device__ __noinline__ int stage_collision(double* ws, int* wi, int lane, int* 
   double* con = ws + L.con;
   int *cb1 = wi + L.i_cb1, *cb2 = wi + L.i_cb2, *cdim = wi + L.i_cdim, *cpair = wi + L.i_cpair;
   int ncon = 0;
+#ifdef GE_DIAG
+  int dg_na = 0, dg_k = 0, dg_nhit = 0, dg_nslots = 0, dg_maxn = 0;
+#endif
   // ---- analytic pairs
   for (int base = 0; base < ncand; base += GE_LANES) {
     int ci = base + lane;
@@ -795,6 +798,10 @@ __device__ __noinline__ int stage_collision(double* ws, int* wi, int lane, int* 
       else if (t1 == G_CAPSULE && t2 == G_CAPSULE) col_capsule_capsule(ws, g1, g2, margin, pc);
     }
     // ordered compaction of the per-lane contact lists
+#ifdef GE_DIAG
+    if (pc.n > dg_maxn) dg_maxn = pc.n;
+    if (pc.n < 0 || pc.n > 8) printf("DIAG pc.n %d lane %d block %d pair %d\n", pc.n, lane, (int)blockIdx.x, p);
+#endif
     int total;
     int off = ncon + group_exscan(pc.n, lane, total);
     for (int k = 0; k < pc.n; k++) {
@@ -806,6 +813,9 @@ __device__ __noinline__ int stage_collision(double* ws, int* wi, int lane, int* 
     }
     ncon += total;
   }
+#ifdef GE_DIAG
+  dg_na = ncon;
+#endif
   if (ncon > L.maxcon) { ncon = L.maxcon; *status |= 1; }
   gsync();
   // ---- convex pairs through MPR
@@ -875,15 +885,28 @@ __device__ __noinline__ int stage_collision(double* ws, int* wi, int lane, int* 
       }
     }
     const int out = ncon + nhit;
+#ifdef GE_DIAG
+    dg_k = k; dg_nhit = nhit; dg_nslots = nslots;
+#endif
     if (overflow) *status |= 1;
     ncon = out;
     gsync();
   }
 #endif
   // ---- per-contact frame and solver parameters
+  bool bad_pair = false;
   LANE_LOOP(i, ncon) {
     double* c = con + i * L.cstride;
     int p = cpair[i];
+#ifdef GE_DIAG
+    if ((unsigned)p >= (unsigned)m.npair)
+      printf("DIAG bad pair index: block %d lane %d i %d p %d ncon %d (analytic total %d, max per lane %d) ncand %d mpr k %d nhit %d nslots %d maxcon %d\n", (int)blockIdx.x,
+             lane, i, p, ncon, dg_na, dg_maxn, ncand, dg_k, dg_nhit, dg_nslots, L.maxcon);
+#endif
+    // Safety net (r02m): a contact record whose pair index is not a pair of the model must never be dereferenced - the record is
+    // neutralised (pair 0, far outside its margin: no force) and the environment flagged (status bit 6 = 64, below).  See DESIGN.md
+    // section 4 for the open issue this guards.
+    if ((unsigned)p >= (unsigned)m.npair) { bad_pair = true; p = 0; cpair[i] = 0; c[C_DIST] = 1e3; }
     make_frame(c + C_FRAME);
     int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1], b1 = m.geom_bodyid[g1], b2 = m.geom_bodyid[g2], dim = m.pair_condim[p];
     cb1[i] = b1; cb2[i] = b2; cdim[i] = dim;
@@ -910,6 +933,7 @@ __device__ __noinline__ int stage_collision(double* ws, int* wi, int lane, int* 
     if (dim > 1) { R = 2 * mu[0] * mu[0] / m.impratio * R; if (R < GE_MINVAL) R = GE_MINVAL; }
     c[C_D] = 1.0 / R; c[C_B] = B; c[C_KR] = K * imp * (dist - margin);
   }
+  if (group_any(bad_pair)) *status |= 64;  // (every thread keeps its own copy of the status word: the flag has to be set by all of them)
   gsync();
   return ncon;
 }

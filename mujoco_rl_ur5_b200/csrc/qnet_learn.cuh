@@ -98,32 +98,51 @@ __global__ void k_reduce_rows(const float* __restrict__ part, float* __restrict_
 __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const bf16* __restrict__ dY, const bf16* __restrict__ act, const float* __restrict__ o,
                                                        const float* __restrict__ stats, int rows, int C, int HW, float eps, int rows_per_cta,
                                                        bf16* __restrict__ dpre_out, float* __restrict__ part) {
-  // thread t handles channels t, t + 256, ...; consecutive threads read consecutive channels of a row (coalesced)
+  // 256 threads = Cw channels x RL row lanes (Cw = min(C, 256)): consecutive threads read consecutive channels of a row (coalesced), row lane
+  // rl takes rows r0 + rl, r0 + rl + RL, ...; the row lanes are added in fixed order through shared memory.  (r02k: with one thread per
+  // channel only 64 / 128 of the 256 threads worked in the 64- / 128-channel layers.)
+  __shared__ float sh[2][256];
   const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float s1 = stats[(size_t)c * 2], s2 = stats[(size_t)c * 2 + 1];  // image 0's entry = batch value after the merge
-    const float mean = s1 / HW, var = fmaxf(s2 / HW - mean * mean, 0.f), rstd = rsqrtf(var + eps);
+  for (int cb = 0; cb < C; cb += 256) {
+    const int Cw = min(C - cb, 256), RL = 256 / Cw, c = cb + (int)threadIdx.x % Cw, rl = (int)threadIdx.x / Cw;
     float a1 = 0.f, a2 = 0.f;
-    for (int r = r0; r < r1; r++) {
-      const size_t i = (size_t)r * C + c;
-      const float d = __bfloat162float(act[i]) > 0.f ? __bfloat162float(dY[i]) : 0.f;
-      if (dpre_out) dpre_out[i] = __float2bfloat16(d);
-      a1 += d;
-      a2 += d * ((o[i] - mean) * rstd);
+    if (rl < RL) {
+      const float s1 = stats[(size_t)c * 2], s2 = stats[(size_t)c * 2 + 1];  // image 0's entry = batch value after the merge
+      const float mean = s1 / HW, var = fmaxf(s2 / HW - mean * mean, 0.f), rstd = rsqrtf(var + eps);
+      for (int r = r0 + rl; r < r1; r += RL) {
+        const size_t i = (size_t)r * C + c;
+        const float d = __bfloat162float(act[i]) > 0.f ? __bfloat162float(dY[i]) : 0.f;
+        if (dpre_out) dpre_out[i] = __float2bfloat16(d);
+        a1 += d;
+        a2 += d * ((o[i] - mean) * rstd);
+      }
     }
-    part[((size_t)blockIdx.x * C + c) * 2] = a1;
-    part[((size_t)blockIdx.x * C + c) * 2 + 1] = a2;
+    sh[0][threadIdx.x] = a1; sh[1][threadIdx.x] = a2;
+    __syncthreads();
+    if ((int)threadIdx.x < Cw) {
+      float t1 = 0.f, t2 = 0.f;
+      for (int k = 0; k < RL; k++) { t1 += sh[0][k * Cw + threadIdx.x]; t2 += sh[1][k * Cw + threadIdx.x]; }
+      part[((size_t)blockIdx.x * C + cb + threadIdx.x) * 2] = t1;
+      part[((size_t)blockIdx.x * C + cb + threadIdx.x) * 2 + 1] = t2;
+    }
+    __syncthreads();
   }
 }
-// sums[C,2] = per-channel totals of the partials in CTA order; dgamma[c] = sums[c][1], dbeta[c] = sums[c][0]
-__global__ void k_bn_bwd_sums(const float* __restrict__ part, int nparts, int C, float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+// sums[C,2] = per-channel totals of the partials; dgamma[c] = sums[c][1], dbeta[c] = sums[c][0].  One warp per channel: lane l adds parts
+// l, l + 32, ... in order, then a fixed butterfly over the lanes (deterministic; r02k: one THREAD per channel walked ~1000 partials and
+// the 24 launches took 0.8 ms of a 9 ms update).
+__global__ void __launch_bounds__(128) k_bn_bwd_sums(const float* __restrict__ part, int nparts, int C, float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double a1 = 0, a2 = 0;
-  for (int k = 0; k < nparts; k++) { a1 += part[((size_t)k * C + c) * 2]; a2 += part[((size_t)k * C + c) * 2 + 1]; }
-  sums[c * 2] = (float)a1; sums[c * 2 + 1] = (float)a2;
-  if (dgamma) dgamma[c] = (float)a2;
-  if (dbeta) dbeta[c] = (float)a1;
+  for (int k = lane; k < nparts; k += 32) { a1 += part[((size_t)k * C + c) * 2]; a2 += part[((size_t)k * C + c) * 2 + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
+  if (lane == 0) {
+    sums[c * 2] = (float)a1; sums[c * 2 + 1] = (float)a2;
+    if (dgamma) dgamma[c] = (float)a2;
+    if (dbeta) dbeta[c] = (float)a1;
+  }
 }
 __global__ void __launch_bounds__(256) k_bn_bwd_apply(const bf16* __restrict__ dY, const bf16* __restrict__ act, const float* __restrict__ o,
                                                       const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ sums,
@@ -136,6 +155,37 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const bf16* __restrict__ d
   const float xhat = (o[i] - mean) * rstd;
   const float d = __bfloat162float(act[i]) > 0.f ? __bfloat162float(dY[i]) : 0.f;
   d_o[i] = __float2bfloat16(gamma[c] * rstd * (d - sums[c * 2] * invN - xhat * sums[c * 2 + 1] * invN));
+}
+
+// the same, 8 consecutive channels per thread (16-byte loads / stores; C % 8 == 0), identical arithmetic per element
+__global__ void __launch_bounds__(256) k_bn_bwd_apply8(const bf16* __restrict__ dY, const bf16* __restrict__ act, const float* __restrict__ o,
+                                                       const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ sums,
+                                                       size_t n8, int C, int HW, float invN, float eps, bf16* __restrict__ d_o) {
+  size_t i8 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i8 >= n8) return;
+  const size_t i = i8 * 8;
+  const int c0 = (int)(i % C);
+  const uint4 qd = *(const uint4*)(dY + i), qa = *(const uint4*)(act + i);
+  const float4 o0 = *(const float4*)(o + i), o1 = *(const float4*)(o + i + 4);
+  const float ov[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+  const __nv_bfloat162 *pd = (const __nv_bfloat162*)&qd, *pa = (const __nv_bfloat162*)&qa;
+  __nv_bfloat162 out[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const float2 fd = __bfloat1622float2(pd[k]), fa = __bfloat1622float2(pa[k]);
+    float r[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int c = c0 + 2 * k + h;
+      const float s1 = stats[(size_t)c * 2], s2 = stats[(size_t)c * 2 + 1];
+      const float mean = s1 / HW, var = fmaxf(s2 / HW - mean * mean, 0.f), rstd = rsqrtf(var + eps);
+      const float xhat = (ov[2 * k + h] - mean) * rstd;
+      const float d = (h ? fa.y : fa.x) > 0.f ? (h ? fd.y : fd.x) : 0.f;
+      r[h] = gamma[c] * rstd * (d - sums[c * 2] * invN - xhat * sums[c * 2 + 1] * invN);
+    }
+    out[k] = __floats2bfloat162_rn(r[0], r[1]);
+  }
+  *(uint4*)(d_o + i) = *(const uint4*)out;
 }
 
 // ------------------------------------------------------------------------------------------------ weight gradient of a convolution
@@ -218,21 +268,25 @@ __global__ void __launch_bounds__(256) k_conv_first_wgrad(const bf16* __restrict
                                                           int pix_per_cta) {
   __shared__ float red[4][64][37];
   const int co = threadIdx.x & 63, q = threadIdx.x >> 6, HW = H * W, quarter = pix_per_cta / 4;
-  const size_t n = (size_t)B * HW, c0 = (size_t)blockIdx.x * pix_per_cta + (size_t)q * quarter;
-  const size_t i0 = c0 < n ? c0 : n, i1 = c0 + quarter < n ? c0 + quarter : n;
+  const long long n = (long long)B * HW, c0 = (long long)blockIdx.x * pix_per_cta + (long long)q * quarter;
+  const int i0 = (int)(c0 < n ? c0 : n), i1 = (int)(c0 + quarter < n ? c0 + quarter : n);  // (B * H * W < 2^31: checked by the caller)
   float acc[36];
 #pragma unroll
   for (int j = 0; j < 36; j++) acc[j] = 0.f;
-  for (size_t i = i0; i < i1; i++) {
-    const int b = (int)(i / HW), p = (int)(i % HW), oh = p / W, ow = p % W;
-    const float d = __bfloat162float(dY[i * 64 + co]);
+  int b = i0 / HW, p = i0 - b * HW, oh = p / W, ow = p - oh * W;  // walked incrementally: no division in the loop
+  const bf16* dp = dY + (size_t)i0 * 64 + co;
+  for (int i = i0; i < i1; i++, dp += 64) {
+    const float d = __bfloat162float(*dp);
+    const float* xb = x + (size_t)b * 4 * HW;
 #pragma unroll
     for (int tap = 0; tap < 9; tap++) {
       const int ih = oh + tap / 3 - 1, iw = ow + tap % 3 - 1;
       if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+      const float* xp = xb + ih * W + iw;
 #pragma unroll
-      for (int c = 0; c < 4; c++) acc[tap * 4 + c] += d * __ldg(x + ((size_t)(b * 4 + c) * H + ih) * W + iw);
+      for (int c = 0; c < 4; c++) acc[tap * 4 + c] += d * __ldg(xp + c * HW);
     }
+    if (++ow == W) { ow = 0; if (++oh == H) { oh = 0; b++; } }
   }
 #pragma unroll
   for (int j = 0; j < 36; j++) red[q][co][j] = acc[j];
@@ -267,6 +321,49 @@ __global__ void k_maxpool_bwd(const bf16* __restrict__ x, const bf16* __restrict
       if (bh == ih && bw == iw) g += __bfloat162float(dY[(((size_t)b * OH + oh) * OW + ow) * C + c]);
     }
   dX[i] = __float2bfloat16(g);
+}
+// the same, 8 channels per thread (16-byte loads; C % 8 == 0): identical arithmetic and window order, an eighth of the load instructions
+// (r02h: the scalar kernel took 1.5 ms of an update for the two pools)
+__global__ void __launch_bounds__(256) k_maxpool_bwd8(const bf16* __restrict__ x, const bf16* __restrict__ dY, bf16* __restrict__ dX, int B, int H, int W, int C) {
+  const int OH = (H + 1) / 2, OW = (W + 1) / 2, C8 = C / 8;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)B * H * W * C8;
+  if (i >= n) return;
+  const int c8 = (int)(i % C8), iw = (int)((i / C8) % W), ih = (int)((i / ((size_t)C8 * W)) % H), b = (int)(i / ((size_t)C8 * W * H));
+  float g[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) g[k] = 0.f;
+  for (int oh = ih / 2; oh <= (ih + 1) / 2 && oh < OH; oh++)
+    for (int ow = iw / 2; ow <= (iw + 1) / 2 && ow < OW; ow++) {
+      float best[8]; int bpos[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) { best[k] = -3.0e38f; bpos[k] = -1; }
+      for (int kh = 0; kh < 3; kh++)
+        for (int kw = 0; kw < 3; kw++) {
+          const int hh = oh * 2 - 1 + kh, ww = ow * 2 - 1 + kw;
+          if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+          const uint4 q = *(const uint4*)(x + (((size_t)b * H + hh) * W + ww) * C + c8 * 8);
+          const __nv_bfloat162* p2 = (const __nv_bfloat162*)&q;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const float2 f = __bfloat1622float2(p2[k]);
+            if (f.x > best[2 * k]) { best[2 * k] = f.x; bpos[2 * k] = kh * 3 + kw; }
+            if (f.y > best[2 * k + 1]) { best[2 * k + 1] = f.y; bpos[2 * k + 1] = kh * 3 + kw; }
+          }
+        }
+      const int mine = (ih - (oh * 2 - 1)) * 3 + (iw - (ow * 2 - 1));  // where (ih, iw) sits in this window
+      const uint4 dq = *(const uint4*)(dY + (((size_t)b * OH + oh) * OW + ow) * C + c8 * 8);
+      const __nv_bfloat162* d2 = (const __nv_bfloat162*)&dq;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float2 f = __bfloat1622float2(d2[k]);
+        if (bpos[2 * k] == mine) g[2 * k] += f.x;
+        if (bpos[2 * k + 1] == mine) g[2 * k + 1] += f.y;
+      }
+    }
+  __nv_bfloat162 o[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) o[k] = __floats2bfloat162_rn(g[2 * k], g[2 * k + 1]);
+  *(uint4*)(dX + i * 8) = *(const uint4*)o;
 }
 // UpsamplingBilinear2d(scale 2, align_corners=True) backward in gather form: input pixel (ih, iw) collects w * dY from the output pixels
 // whose 2x2 footprint contains it.  dY [B,2H,2W,C] bf16 -> dX [B,H,W,C] bf16
@@ -354,10 +451,14 @@ extern "C" int gq_bn_relu_bwd(const void* dY, const void* act, const float* o, c
   cudaStream_t st = (cudaStream_t)stream;
   const int rows = B * HW, rpc = 128, nparts = (rows + rpc - 1) / rpc;
   k_bn_bwd_reduce<<<nparts, 256, 0, st>>>((const bf16*)dY, (const bf16*)act, o, stats, rows, C, HW, eps, rpc, (bf16*)dpre_out, scratch_part);
-  k_bn_bwd_sums<<<(C + 127) / 128, 128, 0, st>>>(scratch_part, nparts, C, scratch_sums, dgamma, dbeta);
+  k_bn_bwd_sums<<<(C + 3) / 4, 128, 0, st>>>(scratch_part, nparts, C, scratch_sums, dgamma, dbeta);
   const size_t n = (size_t)rows * C;
-  k_bn_bwd_apply<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const bf16*)dY, (const bf16*)act, o, stats, gamma, scratch_sums, n, C, HW, 1.f / (float)rows, eps,
-                                                                (bf16*)d_o);
+  if (C % 8 == 0)
+    k_bn_bwd_apply8<<<(unsigned)((n / 8 + 255) / 256), 256, 0, st>>>((const bf16*)dY, (const bf16*)act, o, stats, gamma, scratch_sums, n / 8, C, HW, 1.f / (float)rows, eps,
+                                                                       (bf16*)d_o);
+  else
+    k_bn_bwd_apply<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const bf16*)dY, (const bf16*)act, o, stats, gamma, scratch_sums, n, C, HW, 1.f / (float)rows, eps,
+                                                                  (bf16*)d_o);
   QCK(cudaGetLastError());
   return 0;
 }
@@ -527,7 +628,7 @@ extern "C" int gq_conv_wgrad(const void* dY, const void* x, float* scratch_part,
   return 0;
 }
 extern "C" int gq_conv_first_wgrad(const void* dY, const float* x, float* scratch_part, float* dW, int B, int H, int W, void* stream) {
-  if (!dY || !x || !scratch_part || !dW) { snprintf(q_err, sizeof q_err, "gq_conv_first_wgrad: bad argument"); return -1; }
+  if (!dY || !x || !scratch_part || !dW || (long long)B * H * W >= (1LL << 31)) { snprintf(q_err, sizeof q_err, "gq_conv_first_wgrad: bad argument"); return -1; }
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)B * H * W;
   const int ppc = 2048, chunks = (int)((n + ppc - 1) / ppc);
@@ -538,7 +639,8 @@ extern "C" int gq_conv_first_wgrad(const void* dY, const float* x, float* scratc
 }
 extern "C" int gq_maxpool_bwd(const void* x, const void* dY, void* dX, int B, int H, int W, int C, void* stream) {
   const size_t n = (size_t)B * H * W * C;
-  k_maxpool_bwd<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)dY, (bf16*)dX, B, H, W, C);
+  if (C % 8 == 0) k_maxpool_bwd8<<<(unsigned)((n / 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)dY, (bf16*)dX, B, H, W, C);
+  else k_maxpool_bwd<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)dY, (bf16*)dX, B, H, W, C);
   QCK(cudaGetLastError());
   return 0;
 }

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Q-net forward alone (64 synthetic images, seeded weights) — the command ncu captures for the conv / glue kernels.
-usage: [ncu ...] python tools/qnet_profile.py [images] [reps]"""
+usage: [ncu ...] python tools/qnet_profile.py [images] [reps] [chunk]"""
 import os
 import sys
 
@@ -11,8 +11,9 @@ from mujoco_rl_ur5_b200.qnet import QNetForward, make_torch_qnet
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 64
 torch.manual_seed(0)
-qf = QNetForward(make_torch_qnet(6).state_dict(), 0, max_batch=64)
+qf = QNetForward(make_torch_qnet(6).state_dict(), 0, max_batch=chunk)
 g = torch.Generator(device="cuda").manual_seed(1)
 obs = {"rgb": torch.randint(0, 256, (n, 200, 200, 3), dtype=torch.uint8, device="cuda", generator=g),
        "depth": 1.0 + 0.1 * torch.rand((n, 200, 200), device="cuda", generator=g)}
