@@ -266,7 +266,6 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
       if (n == wl) { mydof = e; mysgn = s; }
       n++;
     }
-#if GE_NW > 1  // (the 40-object scene; in the 6-object scene coupled contacts are arm + object with n = 20 > 16 dofs: nothing to share, r02r)
     // The contact touches n dofs (12 for two free bodies), a warp has 32 lanes: P = 32 / n lanes share one row of the n x n update, lane
     // (r, p) takes the columns p, p + P, ...  Every entry still receives exactly one addition per contact, computed in the same order, so
     // the result does not depend on P.  (r02g piled-pile capture: this loop was 19 K of the 55 K warp instructions of a Hessian build.)
@@ -291,22 +290,6 @@ __device__ __noinline__ void build_hessian(double* ws, int* wi, int ncon, int ns
       for (int k = 0; k < dim; k++) h += t[k] * __shfl_sync(FULL, J[k], src);
       if (v && myrow >= rj) Hb[HIDX(myrow, rj)] += h;
     }
-#else
-    double J[6] = {0, 0, 0, 0, 0, 0}, t[6] = {0, 0, 0, 0, 0, 0};
-    int myrow = -1;
-    if (wl < n) {
-      jac_column(c, dim, cdof + 6 * mydof, mysgn, J);
-      weight_column(c, dim, mask, J, t);
-      const int tt = m.dof_treeindex[mydof];
-      myrow = tcount[tt] + mydof - m.tree_dofadr[tt];
-    }
-    for (int j = 0; j < n; j++) {
-      int rj = __shfl_sync(FULL, myrow, j);
-      double h = 0;
-      for (int k = 0; k < dim; k++) h += t[k] * __shfl_sync(FULL, J[k], j);
-      if (wl < n && myrow >= rj) Hb[HIDX(myrow, rj)] += h;
-    }
-#endif
     __syncwarp();
   }
   if (wl == 0)

@@ -906,9 +906,7 @@ __device__ __noinline__ int stage_collision(double* ws, int* wi, int lane, int* 
     // Safety net (r02m): a contact record whose pair index is not a pair of the model must never be dereferenced - the record is
     // neutralised (pair 0, far outside its margin: no force) and the environment flagged (status bit 6 = 64, below).  See DESIGN.md
     // section 4 for the open issue this guards.
-#if GE_NW > 1 || !defined(GE_NO_GUARD_V0)
     if ((unsigned)p >= (unsigned)m.npair) { bad_pair = true; p = 0; cpair[i] = 0; c[C_DIST] = 1e3; }
-#endif
     make_frame(c + C_FRAME);
     int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1], b1 = m.geom_bodyid[g1], b2 = m.geom_bodyid[g2], dim = m.pair_condim[p];
     cb1[i] = b1; cb2[i] = b2; cdim[i] = dim;
@@ -935,10 +933,7 @@ __device__ __noinline__ int stage_collision(double* ws, int* wi, int lane, int* 
     if (dim > 1) { R = 2 * mu[0] * mu[0] / m.impratio * R; if (R < GE_MINVAL) R = GE_MINVAL; }
     c[C_D] = 1.0 / R; c[C_B] = B; c[C_KR] = K * imp * (dist - margin);
   }
-#if GE_NW > 1 || !defined(GE_NO_GUARD_V0)
-  if (group_any(bad_pair)) *status |= 64;
-#endif
-   // (every thread keeps its own copy of the status word: the flag has to be set by all of them)
+  if (group_any(bad_pair)) *status |= 64;  // (every thread keeps its own copy of the status word: the flag has to be set by all of them)
   gsync();
   return ncon;
 }
