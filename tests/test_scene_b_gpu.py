@@ -215,3 +215,16 @@ def test_scene_b_grasp_attempt_parity(scene_b):
     assert np.abs(gq[:8] - o.qpos[:8]).max() < 1e-4
     assert np.median(np.abs(gq - o.qpos)) < 1e-6
     o.close()
+
+
+@pytest.mark.xfail(strict=False, reason="open defect of the CTA-per-env build (DESIGN.md section 4, r02k-r02q): whole grasp attempts of 1024 scene-B "
+                   "environments with the action set bench.py drew in r02k end in an illegal memory access inside k_run (index arrays of the int "
+                   "workspace overwritten); five other action sets run clean.  Runs in a child process: a CUDA fault must not poison this one.")
+def test_whole_grasp_attempts_at_1024_envs_known_action_set():
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "repro_config5.py"), "1024", "1", "0", "bench"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-500:], [l for l in r.stderr.splitlines() if "rror" in l][-3:])
+    assert "flagged envs 0" in r.stdout, r.stdout[-500:]
