@@ -8,9 +8,9 @@ Headline workload: scene A (UR5gripper_2_finger.xml), 4096 envs per GPU, physics
 (BASELINE configs[1]/[2] scene and env count); `e2e` goes through BatchedGraspEnv.step (host actions in, pixel_2_world,
 whole attempts, 200x200 RGB-D render, host rewards AND the observation copied to pinned host memory, as the reference's API
 hands it to its caller).  Extra objects on the same JSON line (not the headline): `configs` = BASELINE configs 3, 4, 5 as
-specified, `qnet` = the a16 forward alone.
+specified (config 5 runs in a child process per rank), `qnet` = the a16 forward alone, `learner` = one learn() update.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--legs 3,4,5,qnet]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--legs 3,4,5,qnet,learn]
 Under torchrun every rank owns one GPU and its own envs (weak scaling, no data-path collective).
 """
 import argparse
